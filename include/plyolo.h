@@ -1,0 +1,133 @@
+/*
+ * plyolo.h — C ABI of the B200-native YOLOX detection hot path (libplyolo.so).
+ *
+ * The reference (Iywie/pl_YOLO) has no plugin / FFI layer: its boundary for this path is a set
+ * of Python call signatures.  Each entry point below replaces the body of one of
+ * them; the Python shims in pl_yolo_b200/ keep the reference signatures and call these through
+ * ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller unless its name starts with `host_`
+ *     or the comment says "host array"; nothing is allocated or freed inside;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and never synchronises;
+ *   - return value: PLYOLO_OK or a negative PLYOLO_ERR_* code; plyolo_last_error() gives the
+ *     text for the calling thread; arguments are validated before anything is launched;
+ *   - thread-safe for distinct streams / workspaces; no global mutable state;
+ *   - all tensors are contiguous fp32 unless stated; layouts in [] are row-major.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Arithmetic contract: fp32 IEEE, one rounding per reference op (compiled -fmad=false, no
+ * fast-math; libdevice expf/logf/log1pf/sqrtf and IEEE division exactly as ATen's CUDA kernels),
+ * ties broken by lowest index.  `flavor` selects which build of torchvision's NMS arithmetic is
+ * reproduced (PLYOLO_FLAVOR_*).
+ */
+#ifndef PLYOLO_H_
+#define PLYOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLYOLO_VERSION 100 /* 0.1.0 */
+
+#define PLYOLO_OK 0
+#define PLYOLO_ERR_INVALID (-1)     /* bad argument (null pointer, bad shape, unsupported size) */
+#define PLYOLO_ERR_WORKSPACE (-2)   /* workspace pointer null / too small / misaligned (256 B) */
+#define PLYOLO_ERR_CUDA (-3)        /* CUDA runtime error at launch; see plyolo_last_error() */
+#define PLYOLO_ERR_NO_DEVICE (-4)   /* no sm_100 device: there is no CPU fallback */
+
+#define PLYOLO_MAX_LEVELS 8
+#define PLYOLO_MAX_CLASSES 91       /* ATen's CUDA reduce tree is reproduced bit-exactly up to 91 inputs */
+
+/* NMS arithmetic flavor: OR of independent bits. 0 reproduces the reference on CUDA tensors
+ * (torchvision 0.26 nms_kernel.cu behind batched_nms' coordinate trick); 7 reproduces the
+ * reference on CPU tensors (nms_kernel.cpp, per-class loop when 4*Nk > 4000). */
+#define PLYOLO_FLAVOR_CUDA 0
+#define PLYOLO_NMS_RULE_CPU 1 /* tv:ops/boxes.py:80 — per-class NMS on un-offset boxes when 4*Nk > 4000 */
+#define PLYOLO_IOU_NOFMA 2    /* union = (Sa + Sb) - inter, Sb rounded (CPU kernel); default fuses Sb: fma(wb,hb,Sa) */
+#define PLYOLO_THR_F64 4      /* fp32 IoU compared against the double threshold (CPU kernel) */
+#define PLYOLO_FLAVOR_CPU 7
+
+typedef void *plyolo_stream_t; /* cudaStream_t */
+
+int plyolo_version(void);
+const char *plyolo_last_error(void);
+/* number of kernels the calling thread has launched through this library so far (bench accounting) */
+unsigned long long plyolo_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * decode — replaces YOLOXLoss.decode (models/losses/yolox/yolox_loss.py:175-228) and, with
+ * inference != 0, also the eval branch of YOLOXLoss.__call__ (:25-36), i.e. all of
+ * YOLOXDecoder.__call__ (models/losses/yolox/yolox_decoder.py:16-58).
+ *   host_lvl   host array of n_levels device pointers, level l = [B, 5+C, hs[l], ws[l]]
+ *              (channels reg(4)|obj|cls(C), models/heads/decoupled_head.py:93)
+ *   hs, ws, strides   host arrays [n_levels]; hs[l] == ws[l] is required (reference quirk Q2b)
+ *   preds      [B, A, 5+C], A = sum hs*ws.  inference == 0: (cx,cy,w,h, raw obj, raw cls);
+ *              inference != 0: (x1,y1,x2,y2, sigmoid(obj), sigmoid(cls))
+ *   ori_boxes  [B, A, 4] raw regression outputs (yolox_loss.py:214) or NULL
+ * The head maps are not modified (the reference's in-place aliasing, quirk Q1, is not reproduced).
+ * ------------------------------------------------------------------------------------------- */
+int plyolo_decode_f32(const float *const *host_lvl, const int *hs, const int *ws, const int *strides,
+                      int n_levels, int B, int C, float *preds, float *ori_boxes, int inference,
+                      plyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * postprocess — replaces postprocess / demo_postprocess (models/evaluators/postprocess.py:7-48,
+ * :51-92) including torchvision.ops.batched_nms / nms (tv:ops/boxes.py:51-120, torchvision::nms).
+ *   preds      [B, A, 5+C] inference-mode predictions (x1,y1,x2,y2,obj,cls..)
+ *   conf_thre, nms_thre   the Python floats the reference receives (doubles; compared as the
+ *              reference compares them: conf in fp32, IoU per `flavor`)
+ *   max_nms    10000 in the reference (:9): the FIRST max_nms candidates in anchor order survive
+ *   max_det    300 in the reference (:8)
+ *   dets       [B, max_det, 6] rows (x1,y1,x2,y2,conf,class) score-descending, zero padded
+ *   counts     [B] int32, rows valid per image (0 <=> the reference's None entry)
+ *   keep_idx   [B, max_det] int32 anchor index of every detection (-1 padded) or NULL
+ * Workspace: plyolo_postprocess_workspace_bytes(B, A); 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t plyolo_postprocess_workspace_bytes(int B, int A);
+int plyolo_postprocess_f32(const float *preds, int B, int A, int C, double conf_thre, double nms_thre,
+                           int class_agnostic, int max_nms, int max_det, int flavor, float *dets,
+                           int32_t *counts, int32_t *keep_idx, void *workspace, size_t workspace_bytes,
+                           plyolo_stream_t stream);
+
+/* Fused decode + postprocess straight from the head maps (reads them once, never materialises
+ * preds): what `postprocess(model(imgs, labels), conf, nms)` computes in validation_step
+ * (PL_Modules/pl_detection.py:73-76).  Arguments as the two calls above. */
+int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
+                                  const int *strides, int n_levels, int B, int C, double conf_thre,
+                                  double nms_thre, int class_agnostic, int max_nms, int max_det,
+                                  int flavor, float *dets, int32_t *counts, int32_t *keep_idx,
+                                  void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SimOTA assignment — replaces the per-image block of YOLOXLoss.__call__ (yolox_loss.py:43-118):
+ * GT prep (:43,:55-65), get_in_boxes_info (:231-315), bboxes_iou(xyxy=False)
+ * (models/layers/losses/iou_loss.py:391-414), the BCE/IoU cost (:84-108) and
+ * dynamic_k_matching (:318-370), for the whole batch in one call.
+ *   preds       [B, A, 5+C] training-mode decode output (cx,cy,w,h, raw obj, raw cls)
+ *   labels      [B, Lmax, 5] rows (class,cx,cy,w,h), valid rows first, zero padded
+ *   fg_mask     [B, A] uint8   final foreground mask (the reference's mutated fg_mask, :361)
+ *   matched_gt  [B, A] int32   matched GT row per anchor, -1 = background
+ *               (matched_gt_inds = matched_gt[fg_mask], ascending anchor order, :363)
+ *   matched_iou [B, A] fp32    IoU with the matched GT, 0 for background (pred_ious_this_matching, :367)
+ *   num_fg      [B] int32      (:358)        num_gt [B] int32 (:43)
+ * Workspace: plyolo_simota_workspace_bytes(B, A, Lmax, n_levels); 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t plyolo_simota_workspace_bytes(int B, int A, int Lmax, int n_levels);
+int plyolo_simota_f32(const float *preds, const float *labels, int B, int A, int C, int Lmax,
+                      const int *hs, const int *ws, const int *strides, int n_levels, uint8_t *fg_mask,
+                      int32_t *matched_gt, float *matched_iou, int32_t *num_fg, int32_t *num_gt,
+                      void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+
+/* pairwise IoU — replaces bboxes_iou (models/layers/losses/iou_loss.py:391-414).
+ *   a [na,4], b [nb,4] -> out [na,nb]; xyxy != 0: corner format, else (cx,cy,w,h). */
+int plyolo_bboxes_iou_f32(const float *a, int na, const float *b, int nb, int xyxy, float *out,
+                          plyolo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLYOLO_H_ */

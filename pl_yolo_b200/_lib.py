@@ -1,0 +1,79 @@
+"""ctypes binding of libplyolo.so (include/plyolo.h).  No CPU fallback: if the library is missing
+and cannot be built, importing the ops raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint8, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libplyolo.so")
+
+OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
+FLAVOR_CUDA, NMS_RULE_CPU, IOU_NOFMA, THR_F64, FLAVOR_CPU = 0, 1, 2, 4, 7
+MAX_LEVELS = 8
+
+_lib = None
+
+
+class PlyoloError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    vp, ip = c_void_p, POINTER(c_int)
+    lib.plyolo_version.restype = c_int
+    lib.plyolo_last_error.restype = c_char_p
+    lib.plyolo_launch_count.restype = c_ulonglong
+    lib.plyolo_decode_f32.restype = c_int
+    lib.plyolo_decode_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, vp, vp, c_int, vp]
+    lib.plyolo_postprocess_workspace_bytes.restype = c_size_t
+    lib.plyolo_postprocess_workspace_bytes.argtypes = [c_int, c_int]
+    lib.plyolo_postprocess_f32.restype = c_int
+    lib.plyolo_postprocess_f32.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_int,
+                                           vp, vp, vp, vp, c_size_t, vp]
+    lib.plyolo_decode_postprocess_f32.restype = c_int
+    lib.plyolo_decode_postprocess_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, c_double,
+                                                  c_double, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
+    lib.plyolo_simota_workspace_bytes.restype = c_size_t
+    lib.plyolo_simota_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.plyolo_simota_f32.restype = c_int
+    lib.plyolo_simota_f32.argtypes = [vp, vp, c_int, c_int, c_int, c_int, ip, ip, ip, c_int, vp, vp, vp, vp, vp, vp,
+                                      c_size_t, vp]
+    lib.plyolo_bboxes_iou_f32.restype = c_int
+    lib.plyolo_bboxes_iou_f32.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
+
+
+def lib() -> ctypes.CDLL:
+    """Loads (building first if the sources are newer and nvcc is present) the in-tree library."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise PlyoloError(
+                    "libplyolo.so is missing and could not be built (%s). Run `python -m pl_yolo_b200.build` "
+                    "(needs nvcc); there is no CPU or PyTorch fallback for these ops." % (e,)) from e
+        _lib = ctypes.CDLL(SO_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        msg = lib().plyolo_last_error().decode(errors="replace")
+        raise PlyoloError("%s failed (%d): %s" % (what, rc, msg))
+
+
+def launch_count() -> int:
+    return int(lib().plyolo_launch_count())
+
+
+def int_array(values):
+    return (c_int * len(values))(*[int(v) for v in values])
+
+
+def ptr_array(values):
+    return (c_void_p * len(values))(*[int(v) for v in values])

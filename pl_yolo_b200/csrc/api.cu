@@ -1,0 +1,78 @@
+// api.cu — error state, launch accounting and argument helpers shared by the C-ABI entry points.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace plyolo {
+
+static thread_local char g_err[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+
+int check_device() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("no CUDA device: %s (libplyolo has no CPU fallback)", cudaGetErrorString(e));
+        return PLYOLO_ERR_NO_DEVICE;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; libplyolo is built for sm_100a only", dev, major);
+        return PLYOLO_ERR_NO_DEVICE;
+    }
+    return PLYOLO_OK;
+}
+
+int make_levels(Levels &lv, const float *const *host_lvl, const int *hs, const int *ws, const int *strides,
+                int n_levels, int tile) {
+    PLYOLO_REQUIRE(host_lvl && hs && ws && strides, "null level description");
+    PLYOLO_REQUIRE(n_levels >= 1 && n_levels <= PLYOLO_MAX_LEVELS, "n_levels=%d not in [1,%d]", n_levels,
+                   PLYOLO_MAX_LEVELS);
+    int off = 0, t0 = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        PLYOLO_REQUIRE(host_lvl[l] != nullptr, "level %d pointer is null", l);
+        PLYOLO_REQUIRE(hs[l] > 0 && ws[l] > 0 && strides[l] > 0, "level %d has a non-positive dimension", l);
+        // yolox_loss.py:198 builds the grid with indexing='xy' and views it as (h, w): only square maps
+        // decode correctly; refuse the rest instead of reproducing a scrambled grid.
+        PLYOLO_REQUIRE(hs[l] == ws[l], "level %d is %dx%d: the reference decode is only defined for square maps",
+                       l, hs[l], ws[l]);
+        lv.ptr[l] = host_lvl[l];
+        lv.hw[l] = hs[l] * ws[l];
+        lv.w[l] = ws[l];
+        lv.off[l] = off;
+        lv.tile0[l] = t0;
+        lv.stride[l] = (float)strides[l];
+        off += lv.hw[l];
+        t0 += (lv.hw[l] + tile - 1) / tile;
+    }
+    for (int l = n_levels; l < PLYOLO_MAX_LEVELS; ++l) {
+        lv.ptr[l] = nullptr; lv.hw[l] = 0; lv.w[l] = 1; lv.off[l] = off; lv.tile0[l] = t0; lv.stride[l] = 1.f;
+    }
+    lv.tile0[n_levels] = t0;
+    for (int l = n_levels + 1; l <= PLYOLO_MAX_LEVELS; ++l) lv.tile0[l] = t0;
+    lv.n = n_levels;
+    lv.A = off;
+    return PLYOLO_OK;
+}
+
+}  // namespace plyolo
+
+extern "C" {
+
+int plyolo_version(void) { return PLYOLO_VERSION; }
+const char *plyolo_last_error(void) { return plyolo::g_err; }
+unsigned long long plyolo_launch_count(void) { return plyolo::g_launches; }
+
+}  // extern "C"

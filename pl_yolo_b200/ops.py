@@ -1,0 +1,213 @@
+"""torch.library ops `plyolo::*` over the C ABI (include/plyolo.h).
+
+PyTorch is plumbing here: device memory, the current stream and shape checks.  Every op runs
+hand-written sm_100a kernels from libplyolo.so on the caller's current CUDA stream; there is no
+eager / CPU fallback (CPU tensors raise).
+
+Each op exists twice: `<name>_raw` is the plain Python function (lowest host overhead, used by the
+shims) and `<name>` is the same function registered as `torch.ops.plyolo.<name>` with a fake
+(meta) kernel for shape inference under tracing.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_WS: Dict[Tuple[int, int, str], torch.Tensor] = {}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(kind: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Scratch is cached per (device, stream, kind): launches on one stream are ordered, so reuse is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device), kind)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        assert ws.data_ptr() % 256 == 0
+        _WS[key] = ws
+    return ws
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise _lib.PlyoloError("%s is on %s: plyolo ops are CUDA-only (no CPU fallback)" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _levels(inputs: Sequence[torch.Tensor], strides: Sequence[int]):
+    if len(inputs) != len(strides) or not 1 <= len(inputs) <= _lib.MAX_LEVELS:
+        raise ValueError("need one stride per level and 1..%d levels" % _lib.MAX_LEVELS)
+    xs = [_check_cuda_f32(x, "inputs[%d]" % i) for i, x in enumerate(inputs)]
+    B, ch = xs[0].shape[0], xs[0].shape[1]
+    for x in xs:
+        if x.dim() != 4 or x.shape[0] != B or x.shape[1] != ch:
+            raise ValueError("every level must be [B, 5+C, H, W] with the same B and C")
+    hs = [int(x.shape[2]) for x in xs]
+    ws = [int(x.shape[3]) for x in xs]
+    A = sum(h * w for h, w in zip(hs, ws))
+    return xs, B, ch - 5, hs, ws, A
+
+
+# ------------------------------------------------------------------------------------------ decode
+def decode_raw(inputs: List[torch.Tensor], strides: List[int], inference: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """YOLOXLoss.decode (+ eval branch when `inference`): -> (preds [B,A,5+C], ori_boxes [B,A,4])."""
+    xs, B, C, hs, ws, A = _levels(inputs, strides)
+    dev = xs[0].device
+    preds = torch.empty((B, A, 5 + C), dtype=torch.float32, device=dev)
+    ori = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().plyolo_decode_f32(_lib.ptr_array([x.data_ptr() for x in xs]), _lib.int_array(hs),
+                                          _lib.int_array(ws), _lib.int_array(strides), len(xs), B, C,
+                                          preds.data_ptr(), ori.data_ptr(), int(inference), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_decode_f32")
+    return preds, ori
+
+
+decode = torch.library.custom_op("plyolo::decode", decode_raw, mutates_args=())
+
+
+@decode.register_fake
+def _(inputs, strides, inference):
+    B, ch = inputs[0].shape[0], inputs[0].shape[1]
+    A = sum(x.shape[2] * x.shape[3] for x in inputs)
+    return inputs[0].new_empty((B, A, ch)), inputs[0].new_empty((B, A, 4))
+
+
+# ------------------------------------------------------------------------------------- postprocess
+def postprocess_raw(preds: torch.Tensor, conf_thre: float, nms_thre: float, class_agnostic: bool, max_nms: int,
+                max_det: int, flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (dets [B,max_det,6] zero padded, counts [B] i32, keep_idx [B,max_det] i32 anchor ids)."""
+    p = _check_cuda_f32(preds, "preds")
+    if p.dim() != 3 or p.shape[2] < 6:
+        raise ValueError("preds must be [B, A, 5+C]")
+    B, A, ch = p.shape
+    dev = p.device
+    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.plyolo_postprocess_workspace_bytes(B, A)
+        ws = _workspace("post", nbytes, dev)
+        rc = L.plyolo_postprocess_f32(p.data_ptr(), B, A, ch - 5, float(conf_thre), float(nms_thre),
+                                      int(class_agnostic), int(max_nms), int(max_det), int(flavor), dets.data_ptr(),
+                                      counts.data_ptr(), keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_postprocess_f32")
+    return dets, counts, keep
+
+
+postprocess = torch.library.custom_op("plyolo::postprocess", postprocess_raw, mutates_args=())
+
+
+@postprocess.register_fake
+def _(preds, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor):
+    B = preds.shape[0]
+    return (preds.new_empty((B, max_det, 6)), preds.new_empty((B,), dtype=torch.int32),
+            preds.new_empty((B, max_det), dtype=torch.int32))
+
+
+def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_thre: float, nms_thre: float,
+                       class_agnostic: bool, max_nms: int, max_det: int,
+                       flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused decode + postprocess from the head maps (reads them once; preds never materialised)."""
+    xs, B, C, hs, ws_, A = _levels(inputs, strides)
+    dev = xs[0].device
+    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.plyolo_postprocess_workspace_bytes(B, A)
+        ws = _workspace("post", nbytes, dev)
+        rc = L.plyolo_decode_postprocess_f32(_lib.ptr_array([x.data_ptr() for x in xs]), _lib.int_array(hs),
+                                             _lib.int_array(ws_), _lib.int_array(strides), len(xs), B, C,
+                                             float(conf_thre), float(nms_thre), int(class_agnostic), int(max_nms),
+                                             int(max_det), int(flavor), dets.data_ptr(), counts.data_ptr(),
+                                             keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_decode_postprocess_f32")
+    return dets, counts, keep
+
+
+decode_postprocess = torch.library.custom_op("plyolo::decode_postprocess", decode_postprocess_raw, mutates_args=())
+
+
+@decode_postprocess.register_fake
+def _(inputs, strides, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor):
+    B = inputs[0].shape[0]
+    x = inputs[0]
+    return (x.new_empty((B, max_det, 6)), x.new_empty((B,), dtype=torch.int32),
+            x.new_empty((B, max_det), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------------ SimOTA
+def simota_assign_raw(preds: torch.Tensor, labels: torch.Tensor, hw: List[int],
+                  strides: List[int]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """SimOTA for the whole batch.  preds [B,A,5+C] training-mode decode output, labels [B,Lmax,5];
+    hw = [H0, W0, H1, W1, ...].  -> (fg_mask [B,A] bool, matched_gt [B,A] i32 (-1 bg),
+    matched_iou [B,A] f32, num_fg [B] i32, num_gt [B] i32)."""
+    p = _check_cuda_f32(preds, "preds")
+    lab = _check_cuda_f32(labels, "labels")
+    if p.dim() != 3 or lab.dim() != 3 or lab.shape[2] != 5 or lab.shape[0] != p.shape[0]:
+        raise ValueError("preds must be [B,A,5+C] and labels [B,Lmax,5]")
+    B, A, ch = p.shape
+    Lmax = lab.shape[1]
+    hs, ws_ = list(hw[0::2]), list(hw[1::2])
+    dev = p.device
+    fg = torch.empty((B, A), dtype=torch.uint8, device=dev)
+    mg = torch.empty((B, A), dtype=torch.int32, device=dev)
+    mi = torch.empty((B, A), dtype=torch.float32, device=dev)
+    nfg = torch.empty((B,), dtype=torch.int32, device=dev)
+    ngt = torch.empty((B,), dtype=torch.int32, device=dev)
+    if Lmax == 0:
+        fg.zero_(); mg.fill_(-1); mi.zero_(); nfg.zero_(); ngt.zero_()
+        return fg.bool(), mg, mi, nfg, ngt
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.plyolo_simota_workspace_bytes(B, A, Lmax, len(hs))
+        ws = _workspace("simota", nbytes, dev)
+        rc = L.plyolo_simota_f32(p.data_ptr(), lab.data_ptr(), B, A, ch - 5, Lmax, _lib.int_array(hs),
+                                 _lib.int_array(ws_), _lib.int_array(strides), len(hs), fg.data_ptr(), mg.data_ptr(),
+                                 mi.data_ptr(), nfg.data_ptr(), ngt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 _stream_ptr(dev))
+    _lib.check(rc, "plyolo_simota_f32")
+    return fg.view(torch.bool), mg, mi, nfg, ngt
+
+
+simota_assign = torch.library.custom_op("plyolo::simota_assign", simota_assign_raw, mutates_args=())
+
+
+@simota_assign.register_fake
+def _(preds, labels, hw, strides):
+    B, A = preds.shape[0], preds.shape[1]
+    return (preds.new_empty((B, A), dtype=torch.bool), preds.new_empty((B, A), dtype=torch.int32),
+            preds.new_empty((B, A)), preds.new_empty((B,), dtype=torch.int32), preds.new_empty((B,), dtype=torch.int32))
+
+
+# --------------------------------------------------------------------------------------- bboxes_iou
+def bboxes_iou_raw(bboxes_a: torch.Tensor, bboxes_b: torch.Tensor, xyxy: bool) -> torch.Tensor:
+    a = _check_cuda_f32(bboxes_a, "bboxes_a")
+    b = _check_cuda_f32(bboxes_b, "bboxes_b")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.lib().plyolo_bboxes_iou_f32(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], int(xyxy),
+                                              out.data_ptr(), _stream_ptr(a.device))
+    _lib.check(rc, "plyolo_bboxes_iou_f32")
+    return out
+
+
+bboxes_iou = torch.library.custom_op("plyolo::bboxes_iou", bboxes_iou_raw, mutates_args=())
+
+
+@bboxes_iou.register_fake
+def _(bboxes_a, bboxes_b, xyxy):
+    return bboxes_a.new_empty((bboxes_a.shape[0], bboxes_b.shape[0]))
