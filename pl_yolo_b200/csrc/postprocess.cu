@@ -6,15 +6,17 @@
 //   (cp.async.bulk + mbarrier, no register staging):
 //     FUSED : 5+C row copies of 512 B from the channel-planar head maps  -> tile[channel][anchor]
 //     preds : one contiguous copy of 128*(5+C) floats                     -> tile[anchor][channel]
-//   One thread per anchor then takes max/argmax over sigmoid(cls) (first index on ties, T1),
-//   conf = sigmoid(obj) * class_conf, tests conf >= thr in fp32, and the survivors are compacted
-//   IN ANCHOR ORDER (warp ballot + prefix) into the tile's slot range of the candidate arrays.
+//   Pass A (thread per anchor): sigmoid(obj), max raw class logit, a conservative pre-filter that can
+//   only over-admit.  Pass B (4 lanes per admitted anchor): exact max / first argmax over the
+//   sigmoid VALUES (T1), conf = sigmoid(obj) * class_conf, conf >= thr in fp32.  The survivors are
+//   compacted IN ANCHOR ORDER (warp ballot + prefix) into the tile's slot range of the candidate arrays.
 // Stage 2  nms_kernel            one CTA per image, latency-bound.
 //   tile counts -> prefix -> the first max_nms candidates in anchor order (T2) -> 64-bit keys
-//   (~ordered(score) << 32 | slot) -> bitonic sort in shared memory == stable descending sort ->
-//   greedy NMS in chunks of 32 candidates against the kept list (<= max_det, early exit: output
-//   order == score order == sweep order) with torchvision's arithmetic (coordinate-trick offsets,
-//   asymmetric FMA, IEEE division; see `suppresses`).
+//   (~ordered(score) << 32 | slot) -> bitonic sort (register/shuffle steps inside warps, shared
+//   memory only for distances >= 64) == stable descending sort -> greedy NMS in rounds of 128
+//   candidates against the kept list (<= max_det, early exit: output order == score order == sweep
+//   order) with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division;
+//   see `suppresses`).
 #include <cfloat>
 
 #include "common.cuh"
@@ -25,6 +27,9 @@ constexpr int kPpTile = 128;
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kMaxSortCap = 16384;
+constexpr int kRound = 256;  // candidates per NMS round
+constexpr int kSub = kNmsThreads / kRound;  // threads per candidate
+constexpr int kCrossBit = 0x100;  // class word flag: this box must be tested against every class
 
 struct CandWs {
     int *tile_count;    // [B, NT]
@@ -98,51 +103,103 @@ __global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
         __syncthreads();
     }
 
-    // ---- one thread per anchor: class max / argmax, confidence, filter
+    const int lane = tid & 31, warp = tid >> 5;
     bool pass = false;
     float conf = 0.f;
     int cls = 0;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < cnt) {
-        if (FUSED) {
-            const float so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
-            // conf = so * class_conf with class_conf <= 1, and fp32 multiplication is monotone, so
-            // so < thr already decides the filter (exact; skips the 80 class sigmoids)
-            if (so >= p.conf_thr) {
-                float best = sigmoid_ref(tile[5 * kPpTile + tid]);  // :27
-                for (int c = 1; c < p.C; ++c) {
-                    const float s = sigmoid_ref(tile[(5 + c) * kPpTile + tid]);
-                    if (s > best) { best = s; cls = c; }  // postprocess.py:18, first max index
-                }
-                conf = so * best;              // :19
-                pass = conf >= p.conf_thr;     // :20 (fp32 compare)
-                if (pass) {
-                    const int a = a0 + tid;
-                    const int W = p.lv.w[l];
-                    const float s = p.lv.stride[l];
-                    const float cx = (tile[0 * kPpTile + tid] + (float)(a % W)) * s;  // yolox_loss.py:217
-                    const float cy = (tile[1 * kPpTile + tid] + (float)(a / W)) * s;
-                    const float w = expf(tile[2 * kPpTile + tid]) * s;                // :219
-                    const float h = expf(tile[3 * kPpTile + tid]) * s;
-                    box = make_float4(cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2);  // :31-34
-                }
+    int src_t = tid;  // tile-local anchor this thread finally reports
+
+    if (FUSED) {
+        // ---- pass A (one thread per anchor): sigmoid(obj), max raw class logit, conservative pre-filter.
+        // conf = fl(so * max_c sigmoid(x_c)).  sigmoid is monotone up to a few ulp, so with m = max_c x_c:
+        // conf <= so * sigmoid(m) * (1 + 1e-6); anchors with fl(fl(so * sigmoid(m)) * 1.00001f) < thr cannot pass.
+        // Survivors (exactness restored in pass B) are compacted in anchor order.
+        __shared__ unsigned char surv[kPpTile];
+        __shared__ float s_so[kPpTile];
+        __shared__ float s_best[kPpTile];
+        __shared__ int s_cls[kPpTile];
+        bool pre = false;
+        float so = 0.f;
+        if (tid < cnt) {
+            so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
+            if (so >= p.conf_thr) {                     // class_conf <= 1 and fp32 multiply is monotone
+                float m = tile[5 * kPpTile + tid];
+                for (int c = 1; c < p.C; ++c) m = fmaxf(m, tile[(5 + c) * kPpTile + tid]);
+                pre = (so * sigmoid_ref(m)) * 1.00001f >= p.conf_thr;
             }
-        } else {
-            const float *r = tile + tid * ch;
-            float best = r[5];
-            for (int c = 1; c < p.C; ++c) {
-                const float s = r[5 + c];
-                if (s > best) { best = s; cls = c; }
-            }
-            conf = r[4] * best;
-            pass = conf >= p.conf_thr;
-            box = make_float4(r[0], r[1], r[2], r[3]);
         }
+        const unsigned pm = __ballot_sync(0xffffffffu, pre);
+        if (lane == 0) warp_cnt[warp] = __popc(pm);
+        __syncthreads();
+        int sbase = 0, nsurv = 0;
+#pragma unroll
+        for (int w = 0; w < kPpTile / 32; ++w) {
+            if (w < warp) sbase += warp_cnt[w];
+            nsurv += warp_cnt[w];
+        }
+        if (pre) {
+            const int si = sbase + __popc(pm & ((1u << lane) - 1u));
+            surv[si] = (unsigned char)tid;
+            s_so[si] = so;
+        }
+        __syncthreads();
+        // ---- pass B: 4 lanes per survivor, each takes a quarter of the classes: exact max / first argmax
+        // over the sigmoid VALUES (postprocess.py:18 works on the already-squashed tensor; T1)
+        const int cq = (p.C + 3) >> 2;
+        for (int it = 0; it * (kPpTile >> 2) < nsurv; ++it) {
+            const int si = it * (kPpTile >> 2) + (tid >> 2), q = tid & 3;
+            float best = -1.f;
+            int bi = 0x7fffffff;
+            if (si < nsurv) {
+                const int t = surv[si];
+                const int c0 = q * cq, c1 = min(p.C, c0 + cq);
+                for (int c = c0; c < c1; ++c) {
+                    const float v = sigmoid_ref(tile[(5 + c) * kPpTile + t]);  // yolox_loss.py:27
+                    if (v > best) { best = v; bi = c; }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (si < nsurv && q == 0) { s_best[si] = best; s_cls[si] = bi; }
+        }
+        __syncthreads();
+        // ---- final filter + box decode, one thread per survivor (still anchor order)
+        if (tid < nsurv) {
+            src_t = surv[tid];
+            cls = s_cls[tid];
+            conf = s_so[tid] * s_best[tid];    // postprocess.py:19
+            pass = conf >= p.conf_thr;         // :20 (fp32 compare)
+            if (pass) {
+                const int a = a0 + src_t;
+                const int W = p.lv.w[l];
+                const float s = p.lv.stride[l];
+                const float cx = (tile[0 * kPpTile + src_t] + (float)(a % W)) * s;  // yolox_loss.py:217
+                const float cy = (tile[1 * kPpTile + src_t] + (float)(a / W)) * s;
+                const float w = expf(tile[2 * kPpTile + src_t]) * s;                // :219
+                const float h = expf(tile[3 * kPpTile + src_t]) * s;
+                box = make_float4(cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2);  // :31-34
+            }
+        }
+        __syncthreads();  // warp_cnt is reused below
+    } else if (tid < cnt) {
+        const float *r = tile + tid * ch;
+        float best = r[5];
+        for (int c = 1; c < p.C; ++c) {
+            const float s = r[5 + c];
+            if (s > best) { best = s; cls = c; }  // postprocess.py:18, first max index
+        }
+        conf = r[4] * best;
+        pass = conf >= p.conf_thr;
+        box = make_float4(r[0], r[1], r[2], r[3]);
     }
 
     // ---- order-preserving compaction into the tile's slots (postprocess.py:23 keeps anchor order)
     const unsigned m = __ballot_sync(0xffffffffu, pass);
-    const int lane = tid & 31, warp = tid >> 5;
     if (lane == 0) warp_cnt[warp] = __popc(m);
     __syncthreads();
     int base = 0, total = 0;
@@ -155,29 +212,38 @@ __global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
         const size_t slot = ((size_t)b * p.NT + tile_id) * kPpTile + base + __popc(m & ((1u << lane) - 1u));
         p.ws.box[slot] = box;
         p.ws.score[slot] = conf;
-        p.ws.meta[slot] = (anchor_base + tid) | (cls << 24);
+        p.ws.meta[slot] = (anchor_base + src_t) | (cls << 24);
     }
     if (tid == 0) p.ws.tile_count[b * p.NT + tile_id] = total;
 }
 
 // torchvision's IoU test; a = kept (higher-scored, "row") box, b = later ("column") box.
+// Exactly `inter / union > thr` with torchvision's roundings, but the IEEE division only runs inside a
+// +-1e-6 relative band around the threshold: outside it the correctly rounded quotient provably lies
+// on the same side as the (cheap) product test.  No overlap -> quotient 0 -> never above thr >= 0.
 __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, const int flavor, const float thr_f,
                                            const double thr_d) {
     const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
     const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
     const float w = fmaxf(right - left, 0.f), h = fmaxf(bottom - top, 0.f);
     const float inter = w * h;
+    if (!(inter > 0.f) && thr_f >= 0.f) return false;
     const float Sa = (a.z - a.x) * (a.w - a.y);
-    float iou;
+    float u;
     if (!(flavor & PLYOLO_IOU_NOFMA)) {
         // torchvision 0.26 nms_kernel.cu as compiled for sm_100: Sb is contracted into the sum
         // (0 / 20000 near-threshold pairs differ on B200; the un-fused form flips 352 of them)
-        const float t = __fmaf_rn(b.z - b.x, b.w - b.y, Sa);
-        iou = inter / (t - inter);
+        u = __fmaf_rn(b.z - b.x, b.w - b.y, Sa) - inter;
     } else {
         const float Sb = (b.z - b.x) * (b.w - b.y);
-        iou = inter / ((Sa + Sb) - inter);
+        u = (Sa + Sb) - inter;
     }
+    if (u > 0.f && thr_f > 0.f && u < 1e30f && inter > 1e-30f) {
+        const float cut = thr_f * u;
+        if (inter > cut * 1.000001f) return true;
+        if (inter < cut * 0.999999f) return false;
+    }
+    const float iou = inter / u;
     return (flavor & PLYOLO_THR_F64) ? ((double)iou > thr_d) : (iou > thr_f);
 }
 
@@ -198,10 +264,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     int *kept_cls = reinterpret_cast<int *>(kept_box + p.max_det);                            // [max_det]
     int *kept_slot = kept_cls + p.max_det;                                                    // [max_det]
     int *pref = kept_slot + p.max_det;                                                        // [NT+1]
-    __shared__ float4 cbox[32];
-    __shared__ int ccls[32];
-    __shared__ int calive[32];
-    __shared__ unsigned cmask[32];
+    __shared__ float4 cbox[kRound];
+    __shared__ int ccls[kRound];
+    __shared__ int cidx[kRound];
+    __shared__ unsigned cmask[kRound * (kRound / 32)];
+    __shared__ int s_wcnt[kNmsWarps];
     __shared__ float red[kNmsWarps];
     __shared__ int s_nkept, s_total;
 
@@ -230,7 +297,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     }
     __syncthreads();
     const int Nk = min(s_total, p.max_nms);  // postprocess.py:24-25 — first max_nms in anchor order
-    int n_pad = 32;
+    int n_pad = 64;
     while (n_pad < Nk) n_pad <<= 1;
 
     // ---- keys + max coordinate (tv:ops/boxes.py:99 boxes.max())
@@ -257,9 +324,37 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     for (int w = 1; w < kNmsWarps; ++w) mx = fmaxf(mx, red[w]);
     const float span = mx + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
 
-    // ---- bitonic sort ascending on (~score, slot): score descending, ties -> lower slot == stable
-    for (int k = 2; k <= n_pad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    // ---- bitonic sort ascending on (~score, slot): score descending, ties -> lower slot == stable.
+    // Steps with partner distance <= 32 run in registers (each warp owns 64 consecutive keys, two per
+    // lane, exchanged by shuffles); only distances >= 64 go through shared memory with a block barrier.
+    auto local_steps = [&](const int k_lo, const int k_hi, const int j_hi) {
+        // for every 64-key chunk: stages k = k_lo..k_hi (powers of two), steps j = min(k/2, j_hi)..1
+        for (int chunk = warp; chunk < (n_pad >> 6); chunk += kNmsWarps) {
+            const int i0 = (chunk << 6) + lane;
+            unsigned long long a = keys[i0], c = keys[i0 + 32];
+            for (int k = k_lo; k <= k_hi; k <<= 1) {
+                const bool up = (i0 & k) == 0;  // same for i0 + 32 whenever k != 32 ... handled below
+                for (int j = min(k >> 1, j_hi); j > 0; j >>= 1) {
+                    if (j == 32) {
+                        if ((a > c) == up) { const unsigned long long t = a; a = c; c = t; }
+                    } else {
+                        const bool lower = (lane & j) == 0;
+                        const bool upa = (i0 & k) == 0, upc = ((i0 + 32) & k) == 0;
+                        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, j);
+                        const unsigned long long oc = __shfl_xor_sync(0xffffffffu, c, j);
+                        a = (lower == upa) ? (a < oa ? a : oa) : (a > oa ? a : oa);
+                        c = (lower == upc) ? (c < oc ? c : oc) : (c > oc ? c : oc);
+                    }
+                }
+            }
+            keys[i0] = a;
+            keys[i0 + 32] = c;
+        }
+    };
+    local_steps(2, 64, 32);
+    __syncthreads();
+    for (int k = 128; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j >= 64; j >>= 1) {
             for (int i = tid; i < n_pad; i += kNmsThreads) {
                 const int q = i ^ j;
                 if (q > i) {
@@ -270,62 +365,125 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
             }
             __syncthreads();
         }
+        local_steps(k, k, 32);
+        __syncthreads();
     }
 
     // batched_nms branch (tv:ops/boxes.py:80): per-class loop vs coordinate trick
     const bool per_class = !p.agnostic && 4 * (long long)Nk > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
     const bool use_off = !p.agnostic && !per_class;
+    // the same-class shortcut needs offsets that dwarf their own rounding error (ulp(C*span) << 0.5)
+    const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
 
-    // ---- greedy NMS, 32 candidates per round (one warp each)
-    for (int base = 0; base < Nk; base += 32) {
+    // ---- greedy NMS in rounds of kRound candidates (score order), kSub threads per candidate:
+    //   (A) test every candidate of the round against the kept list (<= max_det boxes in shared memory);
+    //   (B) compact the survivors (usually a small fraction: dense clusters die against earlier keeps) and
+    //       build the suppression bit-matrix among survivors only;
+    //   (C) warp 0 sweeps the survivors sequentially over the remaining bits (ffs), appends the keeps,
+    // and the loop exits as soon as max_det boxes are kept (output order == score order == sweep order).
+    for (int base = 0; base < Nk; base += kRound) {
         const int nkept = s_nkept;
         if (nkept >= p.max_det) break;
-        const int c = base + warp;
-        const int nch = min(32, Nk - base);
+        const int nch = min(kRound, Nk - base);
+        const int ci = tid / kSub, sub = tid % kSub;
+        // (A) every thread of a candidate fetches the same record (one broadcast request per candidate)
+        bool sup = false;
         float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
         int cl = 0;
-        bool alive = false;
-        if (c < Nk) {
-            const unsigned slot = (unsigned)(keys[c] & 0xffffffffu);
+        if (ci < nch) {
+            const unsigned slot = (unsigned)(keys[base + ci] & 0xffffffffu);
             bx = p.ws.box[slot0 + slot];
             cl = p.ws.meta[slot0 + slot] >> 24;
             if (use_off) {
-                const float off = (float)cl * span;  // tv:ops/boxes.py:100-101 (separate roundings)
+                // A box of a HIGHER class can reach back into a lower class's offset range only if both its
+                // x1 and y1 lie below -1 (+- rounding); everything else never overlaps another class.
+                if (!filter_ok || (bx.x < -0.5f && bx.y < -0.5f)) cl |= kCrossBit;
+                const float off = (float)(cl & 0xff) * span;  // tv:ops/boxes.py:100-101 (separate roundings)
                 bx.x = bx.x + off; bx.y = bx.y + off; bx.z = bx.z + off; bx.w = bx.w + off;
+            } else if (!per_class) {
+                cl |= kCrossBit;  // class-agnostic: every pair is tested
             }
-            bool sup = false;
-            for (int k = lane; k < nkept; k += 32) {
-                if (per_class && kept_cls[k] != cl) continue;
+            for (int k = sub; k < nkept; k += kSub) {
+                const int kc = kept_cls[k];
+                if (kc != cl && !((kc | cl) & kCrossBit)) continue;  // different class, neither can cross
                 sup |= suppresses(kept_box[k], bx, p.flavor, p.thr_f, p.thr_d);
             }
-            alive = !__any_sync(0xffffffffu, sup);
-            if (lane == 0) { cbox[warp] = bx; ccls[warp] = cl; calive[warp] = alive ? 1 : 0; }
+        }
+#pragma unroll
+        for (int o = 1; o < kSub; o <<= 1) sup |= __shfl_xor_sync(0xffffffffu, sup ? 1 : 0, o) != 0;
+        const bool alive = ci < nch && !sup;
+        // survivors of each warp (lanes with sub == 0 speak for their candidate)
+        const unsigned am = __ballot_sync(0xffffffffu, alive && sub == 0);
+        if (lane == 0) s_wcnt[warp] = __popc(am);
+        __syncthreads();
+        int abase = 0, n_al = 0;
+#pragma unroll
+        for (int w = 0; w < kNmsWarps; ++w) {
+            if (w < warp) abase += s_wcnt[w];
+            n_al += s_wcnt[w];
+        }
+        if (alive && sub == 0) {
+            const int r = abase + __popc(am & ((1u << lane) - 1u));
+            cbox[r] = bx;
+            ccls[r] = cl;
+            cidx[r] = ci;
         }
         __syncthreads();
-        if (c < Nk) {
-            bool s = false;
-            if (lane > warp && lane < nch && !(per_class && ccls[lane] != cl))
-                s = suppresses(bx, cbox[lane], p.flavor, p.thr_f, p.thr_d);
-            const unsigned mrow = __ballot_sync(0xffffffffu, s);
-            if (lane == 0) cmask[warp] = mrow;
+        // (B) row r of the survivor matrix: bit c set <=> survivor r (if kept) suppresses the later survivor c
+        {
+            const int r = tid / kSub;
+            float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+            int rc = 0;
+            if (r < n_al) { rb = cbox[r]; rc = ccls[r]; }
+#pragma unroll
+            for (int w = 0; w < kRound / 32; ++w) {
+                unsigned m = 0u;
+                if (r < n_al && (w << 5) + 31 > r) {
+                    const int c_hi = min(n_al, (w + 1) << 5);
+                    for (int c = (w << 5) + sub; c < c_hi; c += kSub) {
+                        const int cc = ccls[c];
+                        if (c > r && (cc == rc || ((cc | rc) & kCrossBit)) &&
+                            suppresses(rb, cbox[c], p.flavor, p.thr_f, p.thr_d))
+                            m |= 1u << (c & 31);
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o < kSub; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+                if (r < n_al && sub == 0) cmask[r * (kRound / 32) + w] = m;
+            }
         }
         __syncthreads();
         if (warp == 0) {
-            // sequential sweep over the round (every lane computes it redundantly -> no broadcast)
-            unsigned removed = 0, keepm = 0;
+            // (C) lane l < kRound/32 owns word l of the removed / kept bit-vectors over survivor indices
+            unsigned removed_w = 0, keep_w = 0;
+            if (lane < kRound / 32) {
+                const int lo = lane << 5;
+                removed_w = n_al >= lo + 32 ? 0u : (n_al <= lo ? 0xffffffffu : (0xffffffffu << (n_al - lo)));
+            }
             int nk = nkept;
-            for (int i = 0; i < nch; ++i) {
-                if (calive[i] && !((removed >> i) & 1u) && nk < p.max_det) {
-                    keepm |= 1u << i;
-                    removed |= cmask[i];
+            for (int wd = 0; wd < kRound / 32 && nk < p.max_det; ++wd) {
+                while (nk < p.max_det) {
+                    const unsigned avail = ~__shfl_sync(0xffffffffu, removed_w, wd);
+                    if (!avail) break;
+                    const int bit = __ffs(avail) - 1;
+                    const int r = (wd << 5) + bit;
+                    if (lane == wd) { keep_w |= 1u << bit; removed_w |= 1u << bit; }
+                    if (lane < kRound / 32) removed_w |= cmask[r * (kRound / 32) + lane];
                     ++nk;
                 }
             }
-            if (lane < nch && ((keepm >> lane) & 1u)) {
-                const int pos = nkept + __popc(keepm & ((1u << lane) - 1u));
-                kept_box[pos] = cbox[lane];
-                kept_cls[pos] = ccls[lane];
-                kept_slot[pos] = (int)(keys[base + lane] & 0xffffffffu);
+            // append the keeps in order
+            int pos = nkept;
+            for (int wd = 0; wd < kRound / 32; ++wd) {
+                const unsigned kw = __shfl_sync(0xffffffffu, keep_w, wd);
+                if ((kw >> lane) & 1u) {
+                    const int dst = pos + __popc(kw & ((1u << lane) - 1u));
+                    const int r = (wd << 5) + lane;
+                    kept_box[dst] = cbox[r];
+                    kept_cls[dst] = ccls[r];
+                    kept_slot[dst] = (int)(keys[base + cidx[r]] & 0xffffffffu);
+                }
+                pos += __popc(kw);
             }
             if (lane == 0) s_nkept = nk;
         }
@@ -378,7 +536,7 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     np.B = B; np.NT = NT; np.max_nms = max_nms; np.max_det = max_det; np.flavor = flavor;
     np.agnostic = class_agnostic ? 1 : 0;
     np.thr_f = (float)nms_thre; np.thr_d = nms_thre;
-    int cap = 32;
+    int cap = 64;
     const int need = max_nms < A ? max_nms : A;
     while (cap < need) cap <<= 1;
     np.sort_cap = cap;

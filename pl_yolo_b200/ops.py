@@ -84,17 +84,27 @@ def _(inputs, strides, inference):
 
 
 # ------------------------------------------------------------------------------------- postprocess
+def _det_outputs(B: int, max_det: int, dev: torch.device, out):
+    if out is not None:
+        dets, counts, keep = out
+        assert dets.shape == (B, max_det, 6) and dets.dtype == torch.float32 and dets.is_contiguous() and dets.device == dev
+        assert counts.shape == (B,) and counts.dtype == torch.int32 and counts.device == dev
+        assert keep.shape == (B, max_det) and keep.dtype == torch.int32 and keep.is_contiguous() and keep.device == dev
+        return dets, counts, keep
+    return (torch.empty((B, max_det, 6), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+            torch.empty((B, max_det), dtype=torch.int32, device=dev))
+
+
 def postprocess_raw(preds: torch.Tensor, conf_thre: float, nms_thre: float, class_agnostic: bool, max_nms: int,
-                max_det: int, flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> (dets [B,max_det,6] zero padded, counts [B] i32, keep_idx [B,max_det] i32 anchor ids)."""
+                    max_det: int, flavor: int, out=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (dets [B,max_det,6] zero padded, counts [B] i32, keep_idx [B,max_det] i32 anchor ids).
+    `out=(dets, counts, keep_idx)` writes into caller-owned buffers (CUDA-graph friendly)."""
     p = _check_cuda_f32(preds, "preds")
     if p.dim() != 3 or p.shape[2] < 6:
         raise ValueError("preds must be [B, A, 5+C]")
     B, A, ch = p.shape
     dev = p.device
-    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev)
+    dets, counts, keep = _det_outputs(B, max_det, dev, out)
     L = _lib.lib()
     with torch.cuda.device(dev):
         nbytes = L.plyolo_postprocess_workspace_bytes(B, A)
@@ -106,7 +116,12 @@ def postprocess_raw(preds: torch.Tensor, conf_thre: float, nms_thre: float, clas
     return dets, counts, keep
 
 
-postprocess = torch.library.custom_op("plyolo::postprocess", postprocess_raw, mutates_args=())
+def _postprocess_op(preds: torch.Tensor, conf_thre: float, nms_thre: float, class_agnostic: bool, max_nms: int,
+                    max_det: int, flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return postprocess_raw(preds, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor)
+
+
+postprocess = torch.library.custom_op("plyolo::postprocess", _postprocess_op, mutates_args=())
 
 
 @postprocess.register_fake
@@ -117,14 +132,12 @@ def _(preds, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor):
 
 
 def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_thre: float, nms_thre: float,
-                       class_agnostic: bool, max_nms: int, max_det: int,
-                       flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                           class_agnostic: bool, max_nms: int, max_det: int, flavor: int,
+                           out=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Fused decode + postprocess from the head maps (reads them once; preds never materialised)."""
     xs, B, C, hs, ws_, A = _levels(inputs, strides)
     dev = xs[0].device
-    dets = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev)
+    dets, counts, keep = _det_outputs(B, max_det, dev, out)
     L = _lib.lib()
     with torch.cuda.device(dev):
         nbytes = L.plyolo_postprocess_workspace_bytes(B, A)
@@ -138,7 +151,13 @@ def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_
     return dets, counts, keep
 
 
-decode_postprocess = torch.library.custom_op("plyolo::decode_postprocess", decode_postprocess_raw, mutates_args=())
+def _decode_postprocess_op(inputs: List[torch.Tensor], strides: List[int], conf_thre: float, nms_thre: float,
+                           class_agnostic: bool, max_nms: int, max_det: int,
+                           flavor: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return decode_postprocess_raw(inputs, strides, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor)
+
+
+decode_postprocess = torch.library.custom_op("plyolo::decode_postprocess", _decode_postprocess_op, mutates_args=())
 
 
 @decode_postprocess.register_fake
