@@ -226,6 +226,73 @@ def test_postprocess_random_sweep_vs_oracle():
             assert np.array_equal(k.cpu().numpy(), o["keep_idx"]), (it, flavor)
 
 
+def _raw_preds(boxes, scores, classes, A=None, C=80):
+    """eval-mode predictions [1, A, 5+C] holding the given boxes (obj = score, one-hot class = 1)."""
+    n = len(boxes)
+    A = A or n
+    p = np.zeros((1, A, 5 + C), np.float32)
+    p[0, :n, :4] = boxes
+    p[0, :n, 4] = scores
+    p[0, np.arange(n), 5 + np.asarray(classes)] = 1.0
+    return p
+
+
+def _check_post_vs_oracle(p, conf=0.01, nms=0.65, agn=False, flavors=(0, 7), **kw):
+    for flavor in flavors:
+        d, c, k = ops.postprocess_raw(cu(p), conf, nms, agn, kw.get("max_nms", 10000), kw.get("max_det", 300), flavor)
+        o = oracle.postprocess(p, conf, nms, agn, max_nms=kw.get("max_nms", 10000), max_det=kw.get("max_det", 300), flavor=flavor)
+        assert np.array_equal(c.cpu().numpy(), o["counts"]), flavor
+        assert np.array_equal(k.cpu().numpy(), o["keep_idx"]), flavor
+        assert np.array_equal(d.cpu().numpy(), o["dets"]), flavor
+        if flavor == 0 and not kw:  # and the real thing: torchvision's CUDA kernels behind the reference's op chain
+            rd, rc = replay_dets(cu(p), conf, nms, agn)
+            assert np.array_equal(c.cpu().numpy(), rc) and np.array_equal(d.cpu().numpy(), rd)
+    return o
+
+
+def test_postprocess_cross_class_suppression():
+    """Coordinate trick (tv:ops/boxes.py:99-103): a box with negative corners of class c+1 lands on top of a
+    far-corner box of class c and IS suppressed by it on CUDA tensors.  The class-segmented fast path must
+    detect this and hand the image to the exact global sweep."""
+    # span = 401: X' = X + 401 = [301, 301, 406, 406] vs Y = [300, 300, 400, 400] -> IoU 0.873
+    boxes = np.array([[300, 300, 400, 400], [-100, -100, 5, 5], [10, 10, 60, 60]], np.float32)
+    p = _raw_preds(boxes, [0.9, 0.8, 0.7], [0, 1, 5], A=64)
+    o = _check_post_vs_oracle(p, flavors=(0,))
+    assert o["counts"][0] == 2 and 1 not in o["keep_idx"][0, :2].tolist(), "test construction: X must be suppressed across classes"
+    _check_post_vs_oracle(p, flavors=(7,))  # CPU flavor at Nk <= 1000 takes the coordinate trick too
+    # chains: the suppressed cross box would otherwise have suppressed a same-class neighbour
+    boxes = np.array([[300, 300, 400, 400], [-100, -100, 5, 5], [-98, -98, 6, 6], [-60, -60, 30, 30]], np.float32)
+    _check_post_vs_oracle(_raw_preds(boxes, [0.9, 0.8, 0.7, 0.6], [0, 1, 1, 1], A=64))
+    # random corner populations, many classes
+    rng = np.random.default_rng(11)
+    for it in range(8):
+        n = int(rng.integers(50, 600))
+        tl = rng.uniform(-150, -1, (n // 2, 2)); tl = np.concatenate([tl, tl + rng.uniform(2, 160, (n // 2, 2))], 1)
+        M = float(rng.choice([320, 400, 640]))
+        br = M - rng.uniform(0, 150, (n - n // 2, 2)); br = np.concatenate([br - rng.uniform(2, 160, (n - n // 2, 2)), br], 1)
+        boxes = np.concatenate([tl, br]).astype(np.float32)
+        boxes[-1, 2:] = M
+        perm = rng.permutation(n)
+        p = _raw_preds(boxes[perm], rng.uniform(0.05, 1, n).astype(np.float32), rng.integers(0, int(rng.choice([2, 3, 80])), n), A=max(n, 64))
+        _check_post_vs_oracle(p)
+
+
+def test_postprocess_class_segment_shapes():
+    """Class segments of every size (empty, 1, 32, 33, hundreds, > max_det keeps per class), score ties,
+    and candidate counts around the fast path's shared-memory capacity."""
+    rng = np.random.default_rng(12)
+    for n, ncls, spread in [(33, 1, 600), (64, 2, 50), (700, 3, 3000), (2000, 80, 600), (4096, 80, 1200), (4097, 7, 1500),
+                            (5000, 80, 900), (1500, 1, 5000), (900, 2, 20000)]:
+        xy = rng.uniform(0, spread, (n, 2))
+        wh = rng.uniform(4, 80, (n, 2))
+        boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        scores = rng.choice(np.linspace(0.05, 1, 40), n).astype(np.float32)  # many exact score ties
+        p = _raw_preds(boxes, scores, rng.integers(0, ncls, n), A=n)
+        _check_post_vs_oracle(p)
+        _check_post_vs_oracle(p, agn=True, flavors=(0,))
+        _check_post_vs_oracle(p, max_det=50, max_nms=1000, flavors=(0,))
+
+
 def test_postprocess_errors():
     p = torch.zeros(1, 64, 85, device=DEV)
     with pytest.raises(_lib.PlyoloError):
