@@ -70,8 +70,6 @@ constexpr int kMaxSortCap = 16384;
 constexpr int kRound = 256;                 // candidates per round of the general path
 constexpr int kSub = kNmsThreads / kRound;  // threads per candidate
 constexpr int kCrossBit = 0x100;            // class word flag: this box must be tested against every class
-constexpr int kFastCap = 4096;              // fast path: candidates whose offset boxes are staged in shared memory
-constexpr int kMaxCross = 512;              // boxes that may reach into another class's offset range
 constexpr int kMaxClasses = 128;            // class field of the key: 7 bits
 
 // ---- sort keys ----------------------------------------------------------------------------------
@@ -370,6 +368,55 @@ __device__ __forceinline__ void warp_class_nms(const unsigned long long *keys, c
     }
 }
 
+// Same sweep over a segment whose (offset) boxes already sit in box_s[s, e) in score order; the kept boxes
+// are compacted in place to the head of the segment (the write position never passes the chunk being
+// processed, whose boxes are in registers by then).
+__device__ __forceinline__ void warp_class_nms_inplace(float4 *box_s, unsigned *keep_bits, const int s, const int e,
+                                                       const int max_det, const int flavor, const float thr_f,
+                                                       const double thr_d) {
+    const int lane = threadIdx.x & 31;
+    int K = 0;
+    for (int c0 = s; c0 < e && K < max_det; c0 += 32) {
+        const int i = c0 + lane;
+        const bool valid = i < e;
+        const float4 bx = valid ? box_s[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool dead = !valid;
+        for (int k = 0; k < K; k += 4) {
+            if (__all_sync(0xffffffffu, dead)) break;  // dense clusters die against the first keeps
+            // 4 independent tests per trip (entries past K are later boxes of the buffer: masked)
+            const float4 k0 = box_s[s + k], k1 = box_s[s + k + 1], k2 = box_s[s + k + 2], k3 = box_s[s + k + 3];
+            const bool s0 = suppresses(k0, bx, flavor, thr_f, thr_d);
+            const bool s1 = k + 1 < K && suppresses(k1, bx, flavor, thr_f, thr_d);
+            const bool s2 = k + 2 < K && suppresses(k2, bx, flavor, thr_f, thr_d);
+            const bool s3 = k + 3 < K && suppresses(k3, bx, flavor, thr_f, thr_d);
+            dead = dead || s0 || s1 || s2 || s3;
+        }
+        unsigned alive = __ballot_sync(0xffffffffu, !dead);
+        unsigned keepm = 0u;
+        int room = max_det - K;
+        while (alive && room > 0) {
+            const int j = __ffs(alive) - 1;  // lowest surviving lane == best remaining score: kept
+            keepm |= 1u << j;
+            alive &= ~(1u << j);
+            --room;
+            if (!alive) break;
+            const float4 jb = make_float4(__shfl_sync(0xffffffffu, bx.x, j), __shfl_sync(0xffffffffu, bx.y, j),
+                                          __shfl_sync(0xffffffffu, bx.z, j), __shfl_sync(0xffffffffu, bx.w, j));
+            const bool sup = ((alive >> lane) & 1u) && suppresses(jb, bx, flavor, thr_f, thr_d);
+            alive &= ~__ballot_sync(0xffffffffu, sup);
+        }
+        __syncwarp();
+        if ((keepm >> lane) & 1u) box_s[s + K + __popc(keepm & ((1u << lane) - 1u))] = bx;
+        if (lane == 0 && keepm) {
+            const int w = c0 >> 5, sh = c0 & 31;
+            atomicOr(&keep_bits[w], keepm << sh);
+            if (sh && (keepm >> (32 - sh))) atomicOr(&keep_bits[w + 1], keepm >> (32 - sh));
+        }
+        K += __popc(keepm);
+        __syncwarp();
+    }
+}
+
 // writes the image's output rows (postprocess.py:43-46): score order, zero padded to max_det
 template <typename SlotOf>
 __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, const size_t slot0, const int nkept,
@@ -395,7 +442,7 @@ __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, cons
 // The whole NMS of image b by the calling CTA (kNmsThreads threads, all of them must call).
 // smem_raw: nms_smem_bytes(...) bytes of 16-byte aligned dynamic shared memory:
 // (layout: see nms_core_bytes)
-__device__ void nms_image(const NmsParams &p, const int b, unsigned char *smem_raw) {
+__device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned char *smem_raw) {
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);  // [sort_cap] / fast: [fast_cap]
     unsigned char *region = smem_raw + (size_t)p.sort_cap * 8;                    // general path buffers
     float4 *kept_fast = reinterpret_cast<float4 *>(smem_raw + (size_t)p.fast_cap * 8);   // [fast_cap]
@@ -759,6 +806,302 @@ __device__ void nms_image(const NmsParams &p, const int b, unsigned char *smem_r
         __syncthreads();
     }
     write_dets(p, b, slot0, s_nkept, [&](const int i) { return kept_slot[i]; });
+}
+
+// ---- one CTA per (image, class group) -------------------------------------------------------------
+// The score stage bucketed the image's candidates by class group (class & 3), recorded the max
+// coordinate and listed the cross boxes.  When the image qualifies for the fast path (class-aware,
+// not truncated by max_nms, every group <= fast_cap, offsets well separated, cross list complete)
+// the kGroups CTAs of the image sweep their classes independently:
+//   bucket -> class histogram -> counting scatter -> one warp per class (sort, gather + offset boxes
+//   from L2, exact cross-class check against the cross list, greedy sweep) -> kept keys compacted,
+//   block-sorted, published;
+// the image's last CTA to finish merges the kGroups sorted kept lists by rank (binary searches) and
+// writes the first max_det rows.  Anything else — and any image where a cross-class pair suppresses —
+// is handled by one CTA with nms_image (exact general algorithm).
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ int g_cnt[kMaxClasses], g_begin[kMaxClasses], g_cursor[kMaxClasses], g_order[kMaxClasses];
+    __shared__ int g_wbase[kFastCap / 32 + 1];
+    __shared__ int g_next, g_fallback, g_last;
+    __shared__ unsigned x_minx[kMaxClasses], x_miny[kMaxClasses];  // per class: min x1 / y1 of its cross boxes (ordered uint)
+    __shared__ int g_lcount[kGroups + 1];
+    __shared__ float4 x_box[kMaxCross];              // cross boxes, class offset applied
+    __shared__ unsigned long long x_key[kMaxCross];
+    const int g = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = p.NT;
+    const size_t slot0 = (size_t)b * NT * kPpTile;
+    int *ctr = p.ws.ctr + b * kImgCtr;
+    long long *prof = p.prof ? p.prof + ((size_t)b * kGroups + g) * 16 : nullptr;
+#define GPROF(slot) do { if (prof && tid == 0) prof[slot] = clock64(); } while (0)
+    GPROF(0);
+
+    int total = 0, gmax = 0;
+#pragma unroll
+    for (int q = 0; q < kGroups; ++q) {
+        const int c = ctr[q];
+        total += c;
+        gmax = max(gmax, c);
+    }
+    const int xc = ctr[kGroups + 1];
+    const float span = ordered_float((unsigned)ctr[kGroups]) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
+    const bool per_class = !p.agnostic && 4 * (long long)total > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
+    const bool use_off = !p.agnostic && !per_class;
+    const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
+    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && gmax <= p.ws.kept_cap &&
+                      (!use_off || (filter_ok && xc <= kMaxCross));
+    if (!fast) {
+        if (g == 0) {
+            NmsParams q = p;
+            q.prof = nullptr;
+            nms_image(q, b, nms_smem);
+            GPROF(7);
+        }
+        return;
+    }
+
+    // shared memory: keys[fast_cap] u64 | box_s[fast_cap] float4 | stage[fast_cap] u64 (later: kept keys, merge lists)
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(nms_smem);
+    float4 *box_s = reinterpret_cast<float4 *>(nms_smem + (size_t)p.fast_cap * 8);
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(nms_smem + (size_t)p.fast_cap * 24);
+    unsigned *keep_bits = reinterpret_cast<unsigned *>(nms_smem + (size_t)p.fast_cap * 32);  // [fast_cap / 32 + 1]
+
+    const int n = ctr[g];
+    const unsigned long long *bucket = p.ws.gkey + ((size_t)b * kGroups + g) * ((size_t)NT * kPpTile);
+    if (tid < kMaxClasses) g_cnt[tid] = 0;
+    if (tid < kMaxClasses) { x_minx[tid] = 0xffffffffu; x_miny[tid] = 0xffffffffu; }
+    if (tid == 0) { g_next = 0; g_fallback = 0; }
+    for (int i = tid; i < (p.fast_cap >> 5) + 1; i += kNmsThreads) keep_bits[i] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const unsigned long long key = bucket[i];
+        stage[i] = key;
+        atomicAdd(&g_cnt[key_class(key)], 1);
+    }
+    if (use_off && xc > 0 && tid < xc) {
+        float4 x = p.ws.xbox[(size_t)b * kMaxCross + tid];
+        const unsigned long long kx = p.ws.xkey[(size_t)b * kMaxCross + tid];
+        atomicMin(&x_minx[key_class(kx)], float_ordered(x.x));
+        atomicMin(&x_miny[key_class(kx)], float_ordered(x.y));
+        const float offx = (float)key_class(kx) * span;
+        x.x = x.x + offx; x.y = x.y + offx; x.z = x.z + offx; x.w = x.w + offx;
+        x_box[tid] = x;
+        x_key[tid] = kx;
+    }
+    __syncthreads();
+    GPROF(1);
+    // ---- class segments (exclusive prefix of the histogram) and the largest-first class order
+    if (warp == 0) {
+        int c4[4], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c4[u] = g_cnt[lane * 4 + u]; sum += c4[u]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        int run = inc - sum;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { g_begin[lane * 4 + u] = run; g_cursor[lane * 4 + u] = run; run += c4[u]; }
+    } else if (tid >= 32 && tid < 32 + kMaxClasses) {
+        const int c = tid - 32, nc = g_cnt[c];
+        int rank = 0;
+        for (int o = 0; o < kMaxClasses; ++o) {
+            const int m = g_cnt[o];
+            rank += (m > nc || (m == nc && o < c)) ? 1 : 0;
+        }
+        g_order[rank] = c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const unsigned long long key = stage[i];
+        keys[atomicAdd(&g_cursor[key_class(key)], 1)] = key;
+    }
+    __syncthreads();
+    GPROF(2);
+    const bool xcheck = use_off && xc > 0;
+
+    // ---- one warp per class, largest first
+    for (;;) {
+        int oi = 0;
+        if (lane == 0) oi = atomicAdd(&g_next, 1);
+        oi = __shfl_sync(0xffffffffu, oi, 0);
+        if (oi >= kMaxClasses) break;
+        const int c = g_order[oi];
+        const int nc = g_cnt[c];
+        if (nc == 0) break;
+        const int s = g_begin[c];
+        warp_sort(keys + s, nc);
+        const float off = use_off ? (float)c * span : 0.f;  // tv:ops/boxes.py:100 (its own rounding)
+        // A box of class c meets a cross box of a class k > c only if its x2 / y2 exceed
+        // (min x1 / y1 of that class's cross boxes) + (k - c) * span (rounding: < 1): per-class limits.
+        float lim_x = 3.0e38f, lim_y = 3.0e38f;
+        if (xcheck) {
+#pragma unroll
+            for (int u = 0; u < kMaxClasses / 32; ++u) {
+                const int k = lane + 32 * u;
+                const unsigned ox = x_minx[k];
+                if (k > c && ox != 0xffffffffu) {
+                    const float d = (float)(k - c) * span - 1.0f;
+                    lim_x = fminf(lim_x, ordered_float(ox) + d);
+                    lim_y = fminf(lim_y, ordered_float(x_miny[k]) + d);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lim_x = fminf(lim_x, __shfl_xor_sync(0xffffffffu, lim_x, o));
+                lim_y = fminf(lim_y, __shfl_xor_sync(0xffffffffu, lim_y, o));
+            }
+        }
+        for (int i0 = 0; i0 < nc; i0 += 128) {              // 4 independent gathers in flight per lane
+            float4 bx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < nc) bx[u] = p.ws.box[slot0 + key_slot(keys[s + i])];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < nc) {
+                    float4 y = bx[u];
+                    // exact cross-class check: only boxes within |min x1| x |min y1| of the far corner can be reached
+                    if (xcheck && y.z > lim_x && y.w > lim_y) {
+                        const unsigned long long ky = keys[s + i];
+                        float4 yo = y;
+                        yo.x = yo.x + off; yo.y = yo.y + off; yo.z = yo.z + off; yo.w = yo.w + off;
+                        for (int q = 0; q < xc; ++q) {
+                            const unsigned long long kx = x_key[q];
+                            if (key_class(kx) <= c) continue;  // the pair is found from the lower class's side
+                            const float4 x = x_box[q];
+                            if (!(x.x < yo.z && x.y < yo.w && yo.x < x.z && yo.y < x.w)) continue;  // no overlap: quotient 0
+                            const bool x_first = (kx & kOrderMask) < (ky & kOrderMask);
+                            if (x_first ? suppresses(x, yo, p.flavor, p.thr_f, p.thr_d) : suppresses(yo, x, p.flavor, p.thr_f, p.thr_d))
+                                g_fallback = 1;
+                        }
+                    }
+                    y.x = y.x + off; y.y = y.y + off; y.z = y.z + off; y.w = y.w + off;  // tv:ops/boxes.py:101
+                    box_s[s + i] = y;
+                }
+            }
+        }
+        __syncwarp();
+        warp_class_nms_inplace(box_s, keep_bits, s, s + nc, p.max_det, p.flavor, p.thr_f, p.thr_d);
+    }
+    if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 3), (unsigned long long)clock64());
+    __syncthreads();
+    if (tid == 0 && g_fallback) atomicOr(&ctr[kGroups + 3], 1);
+
+    // ---- kept keys of the group: class stripped, compacted, sorted, published
+    unsigned long long *keys2 = stage;
+    const int nwords = (n + 31) >> 5;
+    if (warp == 0) {
+        int c4[4], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int w = lane * 4 + u;
+            c4[u] = w < nwords ? __popc(keep_bits[w]) : 0;
+            sum += c4[u];
+        }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        int run = inc - sum;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { g_wbase[lane * 4 + u] = run; run += c4[u]; }
+        if (lane == 31) g_wbase[kFastCap / 32] = inc;
+    }
+    __syncthreads();
+    const int Kg = g_wbase[kFastCap / 32];
+    for (int i = tid; i < n; i += kNmsThreads) {
+        const unsigned wbits = keep_bits[i >> 5];
+        if ((wbits >> (i & 31)) & 1u)
+            keys2[g_wbase[i >> 5] + __popc(wbits & ((1u << (i & 31)) - 1u))] = keys[i] & kOrderMask;
+    }
+    int n2 = 64;
+    while (n2 < Kg) n2 <<= 1;
+    for (int i = Kg + tid; i < n2; i += kNmsThreads) keys2[i] = ~0ull;
+    __syncthreads();
+    GPROF(4);
+    block_sort(keys2, n2);
+    GPROF(5);
+    unsigned long long *pub = p.ws.kept + ((size_t)b * kGroups + g) * p.ws.kept_cap;
+    for (int i = tid; i < Kg; i += kNmsThreads) pub[i] = keys2[i];
+    if (tid == 0) p.ws.kcount[b * kGroups + g] = Kg;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) g_last = (atomicAdd(&ctr[kGroups + 2], 1) == kGroups - 1) ? 1 : 0;
+    __syncthreads();
+    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = xc; prof[13] = g_last; }
+    GPROF(6);
+    if (!g_last) return;
+    __threadfence();
+    if (__ldcg(&ctr[kGroups + 3])) {
+        // a pair of different classes suppresses: the exact global sweep redoes the image
+        NmsParams q = p;
+        q.prof = nullptr;
+        nms_image(q, b, nms_smem);
+        GPROF(7);
+        if (prof && tid == 0) prof[14] = 1;
+        return;
+    }
+    // ---- merge: rank of a kept key = its position in its own list + the number of smaller keys in the others
+    unsigned long long *lists = reinterpret_cast<unsigned long long *>(nms_smem);  // up to kGroups * fast_cap keys (32 B each slot)
+    if (tid <= kGroups) {
+        int acc = 0;
+        for (int q = 0; q < tid; ++q) acc += __ldcg(&p.ws.kcount[b * kGroups + q]);
+        g_lcount[tid] = acc;  // exclusive prefix; [kGroups] = total
+    }
+    __syncthreads();
+    const int Kt = g_lcount[kGroups];
+    for (int q = 0; q < kGroups; ++q) {
+        const unsigned long long *src = p.ws.kept + ((size_t)b * kGroups + q) * p.ws.kept_cap;
+        const int lo = g_lcount[q], cnt = g_lcount[q + 1] - lo;
+        for (int i = tid; i < cnt; i += kNmsThreads) lists[lo + i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    const int nkept = min(Kt, p.max_det);
+    for (int e = tid; e < Kt; e += kNmsThreads) {
+        int q = 0;
+#pragma unroll
+        for (int u = 1; u < kGroups; ++u) q += (e >= g_lcount[u]) ? 1 : 0;
+        const unsigned long long key = lists[e];
+        int rank = e - g_lcount[q];
+#pragma unroll
+        for (int u = 0; u < kGroups; ++u) {
+            if (u == q) continue;
+            int lo = g_lcount[u], hi = g_lcount[u + 1];  // first position with key' > key (keys are distinct)
+            const int base = lo;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lists[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo - base;
+        }
+        if (rank < nkept) {
+            const int slot = key_slot(key);
+            const float4 bx = p.ws.box[slot0 + slot];
+            const int meta = p.ws.meta[slot0 + slot];
+            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + rank) * 6);
+            d[0] = make_float2(bx.x, bx.y);
+            d[1] = make_float2(bx.z, bx.w);
+            d[2] = make_float2(p.ws.score[slot0 + slot], (float)(meta >> 24));
+            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = meta & 0xffffff;
+        }
+    }
+    for (int i = nkept + tid; i < p.max_det; i += kNmsThreads) {
+        float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
+        d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
+        if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
+    }
+    if (tid == 0) p.counts[b] = nkept;
+    GPROF(7);
+#undef GPROF
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {

@@ -22,12 +22,24 @@
 namespace plyolo {
 
 constexpr int kPpTile = 128;
+constexpr int kGroups = 4;      // class groups per image (class & 3): one NMS CTA each
+constexpr int kMaxCross = 512;  // boxes that may reach into another class's offset range (x1, y1 < -0.5)
+constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
+constexpr int kImgCtr = 8;      // ints per image in the counter block (zeroed before every call)
 
 struct CandWs {
     int *tile_count;    // [B, NT]
     float4 *box;        // [B, NT*128]  original (un-offset) corners
     float *score;       // [B, NT*128]
     int *meta;          // [B, NT*128]  anchor | class << 24
+    // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
+    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | #done CTAs | fallback
+    unsigned long long *gkey;     // [B, kGroups, NT*128]  class << 57 | ~ordered(score) << 25 | slot
+    unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
+    float4 *xbox;                 // [B, kMaxCross]
+    unsigned long long *kept;     // [B, kGroups, kept_cap] kept keys of every group, sorted, class stripped
+    int *kcount;                  // [B, kGroups]
+    int kept_cap;
 };
 
 struct ScoreParams {
@@ -200,13 +212,61 @@ __global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
         if (w < warp) base += warp_cnt[w];
         total += warp_cnt[w];
     }
+    const int islot = tile_id * kPpTile + base + __popc(m & ((1u << lane) - 1u));  // slot inside the image
     if (pass) {
-        const size_t slot = ((size_t)b * p.NT + tile_id) * kPpTile + base + __popc(m & ((1u << lane) - 1u));
+        const size_t slot = (size_t)b * p.NT * kPpTile + islot;
         p.ws.box[slot] = box;
         p.ws.score[slot] = conf;
         p.ws.meta[slot] = (anchor_base + src_t) | (cls << 24);
     }
     if (tid == 0) p.ws.tile_count[b * p.NT + tile_id] = total;
+
+    // ---- class-group buckets for the NMS stage (one CTA per image and group): keys in arrival order, the
+    // image's max coordinate (tv:ops/boxes.py:99) and the boxes that can reach another class's offset range
+    if (total == 0) return;
+    __shared__ int g_wcnt[kPpTile / 32][kGroups];
+    __shared__ int g_base[kGroups];
+    __shared__ float w_max[kPpTile / 32];
+    const int grp = cls & (kGroups - 1);
+    unsigned gm = 0u;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const unsigned mg = __ballot_sync(0xffffffffu, pass && grp == g);
+        if (lane == 0) g_wcnt[warp][g] = __popc(mg);
+        if (grp == g) gm = mg;
+    }
+    float cm = pass ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -3.0e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+    if (lane == 0) w_max[warp] = cm;
+    __syncthreads();
+    int *ctr = p.ws.ctr + b * kImgCtr;
+    if (tid < kGroups) {
+        int n = 0;
+#pragma unroll
+        for (int w = 0; w < kPpTile / 32; ++w) n += g_wcnt[w][tid];
+        g_base[tid] = n ? atomicAdd(&ctr[tid], n) : 0;
+    } else if (tid == 32) {
+        float mx = w_max[0];
+#pragma unroll
+        for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, w_max[w]);
+        atomicMax(reinterpret_cast<unsigned *>(&ctr[kGroups]), float_ordered(mx));
+    }
+    __syncthreads();
+    if (pass) {
+        int pos = g_base[grp] + __popc(gm & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += g_wcnt[w][grp];
+        const unsigned long long key = ((unsigned long long)cls << 57) |
+                                       ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)islot;
+        p.ws.gkey[((size_t)b * kGroups + grp) * ((size_t)p.NT * kPpTile) + pos] = key;
+        if (box.x < -0.5f && box.y < -0.5f) {
+            const int xi = atomicAdd(&ctr[kGroups + 1], 1);
+            if (xi < kMaxCross) {
+                p.ws.xkey[(size_t)b * kMaxCross + xi] = key;
+                p.ws.xbox[(size_t)b * kMaxCross + xi] = box;
+            }
+        }
+    }
 }
 
 }  // namespace plyolo
@@ -220,16 +280,30 @@ static thread_local long long *g_nms_prof = nullptr;
 static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t off = 0;
     const size_t slots = (size_t)B * NT * kPpTile;
+    const int kept_cap = NT * kPpTile < kFastCap ? NT * kPpTile : kFastCap;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    size_t o_ctr = take((size_t)B * kImgCtr * sizeof(int));  // first: zeroed before every call
     size_t o_cnt = take((size_t)B * NT * sizeof(int));
     size_t o_box = take(slots * sizeof(float4));
     size_t o_sc = take(slots * sizeof(float));
     size_t o_meta = take(slots * sizeof(int));
+    size_t o_gkey = take(slots * kGroups * sizeof(unsigned long long));
+    size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
+    size_t o_xbox = take((size_t)B * kMaxCross * sizeof(float4));
+    size_t o_kept = take((size_t)B * kGroups * kept_cap * sizeof(unsigned long long));
+    size_t o_kcnt = take((size_t)B * kGroups * sizeof(int));
     if (ws) {
+        ws->ctr = reinterpret_cast<int *>(base + o_ctr);
         ws->tile_count = reinterpret_cast<int *>(base + o_cnt);
         ws->box = reinterpret_cast<float4 *>(base + o_box);
         ws->score = reinterpret_cast<float *>(base + o_sc);
         ws->meta = reinterpret_cast<int *>(base + o_meta);
+        ws->gkey = reinterpret_cast<unsigned long long *>(base + o_gkey);
+        ws->xkey = reinterpret_cast<unsigned long long *>(base + o_xkey);
+        ws->xbox = reinterpret_cast<float4 *>(base + o_xbox);
+        ws->kept = reinterpret_cast<unsigned long long *>(base + o_kept);
+        ws->kcount = reinterpret_cast<int *>(base + o_kcnt);
+        ws->kept_cap = kept_cap;
     }
     return off;
 }
@@ -252,9 +326,9 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     np.prof = g_nms_prof;
     const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
     PLYOLO_REQUIRE(smem <= 208 * 1024, "nms working set (%zu B) exceeds shared memory", smem);
-    cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nms_kernel<<<B, kNmsThreads, smem, stream>>>(np);
-    PLYOLO_CHECK_LAUNCH("nms_kernel");
+    cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nms_group_kernel<<<dim3(kGroups, B), kNmsThreads, smem, stream>>>(np);
+    PLYOLO_CHECK_LAUNCH("nms_group_kernel");
     return PLYOLO_OK;
 }
 
@@ -306,6 +380,10 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     const size_t smem = (size_t)kPpTile * sp.ch * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)B * kImgCtr * sizeof(int), (cudaStream_t)stream) != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+        return PLYOLO_ERR_CUDA;
+    }
     score_kernel<false><<<dim3(sp.NT, B), kPpTile, smem, (cudaStream_t)stream>>>(sp);
     PLYOLO_CHECK_LAUNCH("score_kernel<preds>");
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
@@ -335,6 +413,10 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     const size_t smem = (size_t)kPpTile * sp.ch * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)B * kImgCtr * sizeof(int), (cudaStream_t)stream) != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+        return PLYOLO_ERR_CUDA;
+    }
     score_kernel<true><<<dim3(sp.NT, B), kPpTile, smem, (cudaStream_t)stream>>>(sp);
     PLYOLO_CHECK_LAUNCH("score_kernel<fused>");
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,

@@ -1,15 +1,15 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of nms_kernel on the bench workload (debug hook plyolo_debug_nms_profile)."""
+"""Per-phase cycle breakdown of nms_group_kernel on the bench workload (debug hook plyolo_debug_nms_profile)."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pl_yolo_b200 import _lib, ops, synth
 
-B = 32
+B, G = 32, 4
 heads = [torch.from_numpy(h).cuda() for h in synth.make_heads(B, 640, 80, seed=int(sys.argv[1]) if len(sys.argv) > 1 else 0)]
 L = _lib.lib()
 L.plyolo_debug_nms_profile.argtypes = [ctypes.c_void_p]
-prof = torch.zeros((B, 16), dtype=torch.int64, device="cuda")
+prof = torch.zeros((B * G, 16), dtype=torch.int64, device="cuda")
 for _ in range(3):
     ops.decode_postprocess_raw(heads, [8, 16, 32], 0.01, 0.65, False, 10000, 300, 0)
 L.plyolo_debug_nms_profile(prof.data_ptr())
@@ -17,15 +17,17 @@ ops.decode_postprocess_raw(heads, [8, 16, 32], 0.01, 0.65, False, 10000, 300, 0)
 torch.cuda.synchronize()
 L.plyolo_debug_nms_profile(None)
 p = prof.cpu().numpy().astype(np.int64)
-p[:, 4] = p[:, 13]  # slot 4 is read before the barrier by the compiler's schedule: use the last warp's exit time
-names = ["prefix", "pass1", "scatter+x", "classes", "compact", "sort2", "output"]
-d = np.diff(p[:, :8], axis=1) / 1965.0  # us at 1965 MHz
-print("phase us (mean / max over images):")
-for i, n in enumerate(names):
-    print("  %-9s %7.2f %7.2f" % (n, d[:, i].mean(), d[:, i].max()))
-print("  total     %7.2f %7.2f" % (d.sum(1).mean(), d.sum(1).max()))
-print("Nk", p[:, 10].tolist())
-print("Kt", p[:, 11].tolist())
-print("ncross", p[:, 12].tolist())
-print("slowest class sweep: us", [round((int(v) >> 32) / 1965.0, 1) for v in p[:, 14]], "n", [int(v) & 0xffffffff for v in p[:, 14]])
-print("slowest class sort : us", [round((int(v) >> 32) / 1965.0, 1) for v in p[:, 15]], "n", [int(v) & 0xffffffff for v in p[:, 15]])
+names = ["stage+hist", "prefix+scatter", "classes", "compact", "sort", "publish", "merge/fallback"]
+t = p[:, :8].copy()
+us = lambda a: a / 1965.0
+d = np.diff(t[:, :7], axis=1)
+print("phase us over (image, group) CTAs: mean / max")
+for i, n in enumerate(names[:6]):
+    print("  %-15s %7.2f %7.2f" % (n, us(d[:, i]).mean(), us(d[:, i]).max()))
+last = p[:, 13] == 1
+print("  %-15s %7.2f %7.2f  (last CTA of each image)" % (names[6], us(t[last, 7] - t[last, 6]).mean(), us(t[last, 7] - t[last, 6]).max()))
+print("  CTA total (to publish)  %7.2f %7.2f" % (us(t[:, 6] - t[:, 0]).mean(), us(t[:, 6] - t[:, 0]).max()))
+print("  last CTA total          %7.2f %7.2f" % (us(t[last, 7] - t[last, 0]).mean(), us(t[last, 7] - t[last, 0]).max()))
+print("n per group", p[:, 10].reshape(B, G).tolist())
+print("kept per group", p[:, 11].reshape(B, G).tolist())
+print("ncross", p[::G, 12].tolist(), "fallback images", int(p[:, 14].sum()))
