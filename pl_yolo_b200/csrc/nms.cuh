@@ -99,6 +99,16 @@ __host__ __device__ inline size_t nms_smem_bytes(const int sort_cap, const int f
            (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned);
 }
 
+// nms_group_kernel: the single-CTA layout (fallback), its own fast layout, or the merge's record lists
+__host__ __device__ inline size_t nms_group_smem_bytes(const int sort_cap, const int fast_cap, const int max_det, const int NT) {
+    size_t m = nms_smem_bytes(sort_cap, fast_cap, max_det, NT);
+    const size_t fast_b = (size_t)fast_cap * 40 + (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned);
+    const size_t merge_b = (size_t)kGroups * max_det * sizeof(KeptRec);
+    if (fast_b > m) m = fast_b;
+    if (merge_b > m) m = merge_b;
+    return (m + 15) & ~(size_t)15;
+}
+
 struct NmsParams {
     int B, NT, max_nms, max_det, flavor, agnostic, sort_cap, fast_cap;
     float thr_f;
@@ -808,22 +818,86 @@ __device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned
     write_dets(p, b, slot0, s_nkept, [&](const int i) { return kept_slot[i]; });
 }
 
+// ---- team sort: 8 warps (256 threads, named barrier `bar_id`) sort one large class segment -----------
+__device__ __forceinline__ void team_barrier(const int bar_id) {
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+}
+
+// Ascending sort of k[0, n) in shared memory by a team of 8 warps: blocks of 32 * E keys are sorted in
+// registers (one block per warp at a time), merge steps with partner distance >= a block go through
+// shared memory, the rest of each merge again in registers.  Same ascending-only network as warp_sort.
+template <int E>
+__device__ __forceinline__ void team_sort_e(unsigned long long *k, const int n, const int tw, const int bar_id) {
+    constexpr int BLK = 32 * E;
+    const int lane = threadIdx.x & 31, tt = tw * 32 + lane;  // thread index inside the team
+    int P = BLK;
+    while (P < n) P <<= 1;
+    for (int b0 = tw * BLK; b0 < n; b0 += 8 * BLK) warp_sort_regs<E>(k + b0, min(BLK, n - b0));
+    team_barrier(bar_id);
+    auto ce = [&](const int i, const int q) {
+        if (q < n) {
+            const unsigned long long x = k[i], y = k[q];
+            if (x > y) { k[i] = y; k[q] = x; }
+        }
+    };
+    for (int kk = 2 * BLK; kk <= P; kk <<= 1) {
+        const int h = kk >> 1;
+        for (int t = tt; t < (P >> 1); t += 256) {
+            const int base = (t / h) * kk, o = t & (h - 1);
+            if (base + o >= n) break;
+            ce(base + o, base + kk - 1 - o);
+        }
+        team_barrier(bar_id);
+        for (int j = h >> 1; j >= BLK; j >>= 1) {
+            for (int t = tt; t < (P >> 1); t += 256) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                if (i >= n) break;
+                ce(i, i | j);
+            }
+            team_barrier(bar_id);
+        }
+        for (int b0 = tw * BLK; b0 < n; b0 += 8 * BLK) {
+            unsigned long long v[E];
+            reg_load<E>(v, k + b0, n - b0, lane);
+            reg_merge_tail<E>(v, lane, 16);  // lane distance 16 == element distance BLK / 2
+            reg_store<E>(v, k + b0, n - b0, lane);
+        }
+        team_barrier(bar_id);
+    }
+}
+
+__device__ __noinline__ void team_sort(unsigned long long *k, const int n, const int tw, const int bar_id) {
+    if (n <= 512) team_sort_e<2>(k, n, tw, bar_id);
+    else if (n <= 1024) team_sort_e<4>(k, n, tw, bar_id);
+    else team_sort_e<8>(k, n, tw, bar_id);
+}
+
+constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a team of 8 warps
+
 // ---- one CTA per (image, class group) -------------------------------------------------------------
 // The score stage bucketed the image's candidates by class group (class & 3), recorded the max
 // coordinate and listed the cross boxes.  When the image qualifies for the fast path (class-aware,
 // not truncated by max_nms, every group <= fast_cap, offsets well separated, cross list complete)
 // the kGroups CTAs of the image sweep their classes independently:
-//   bucket -> class histogram -> counting scatter -> one warp per class (sort, gather + offset boxes
-//   from L2, exact cross-class check against the cross list, greedy sweep) -> kept keys compacted,
-//   block-sorted, published;
-// the image's last CTA to finish merges the kGroups sorted kept lists by rank (binary searches) and
-// writes the first max_det rows.  Anything else — and any image where a cross-class pair suppresses —
-// is handled by one CTA with nms_image (exact general algorithm).
+//   1. bucket -> class histogram -> counting scatter into class segments;
+//   2. sort every segment (large ones by teams of 8 warps, the rest one warp each), gather the boxes
+//      from L2 in sorted order, add the class offset, exact cross-class check against the cross list;
+//   3. greedy sweep, one work item per chunk of 32 boxes, items handed out in (class, chunk) order:
+//      a chunk tests its boxes against the keeps of every earlier chunk of its class as soon as that
+//      chunk is final (flag in shared memory), then settles its own 32 boxes and publishes its keeps —
+//      the chunks of a class pipeline across warps and only the settle step is serial;
+//   4. kept keys compacted, block-sorted, the first max_det published as records (key, box, score, class).
+// The image's last CTA to finish merges the kGroups sorted lists by rank (binary searches) and writes
+// the first max_det rows.  Anything else — and any image where a cross-class pair suppresses — is
+// handled by one CTA with nms_image (exact general algorithm).
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ int g_cnt[kMaxClasses], g_begin[kMaxClasses], g_cursor[kMaxClasses], g_order[kMaxClasses];
+    __shared__ int g_cum[kMaxClasses + 1];             // first sweep item of the oi-th largest class
+    __shared__ volatile int g_fin[kMaxClasses];        // chunks of the class that are final
+    __shared__ volatile int g_kcum[kFastCap / 32 + kMaxClasses];  // per sweep item: keeps of its class up to and including it
     __shared__ int g_wbase[kFastCap / 32 + 1];
-    __shared__ int g_next, g_fallback, g_last;
+    __shared__ int g_next, g_next2, g_fallback, g_last, g_nbig;
     __shared__ unsigned x_minx[kMaxClasses], x_miny[kMaxClasses];  // per class: min x1 / y1 of its cross boxes (ordered uint)
     __shared__ int g_lcount[kGroups + 1];
     __shared__ float4 x_box[kMaxCross];              // cross boxes, class offset applied
@@ -849,7 +923,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
     const bool per_class = !p.agnostic && 4 * (long long)total > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
     const bool use_off = !p.agnostic && !per_class;
     const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
-    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && gmax <= p.ws.kept_cap &&
+    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && p.max_det <= kRecCap &&
                       (!use_off || (filter_ok && xc <= kMaxCross));
     if (!fast) {
         if (g == 0) {
@@ -861,17 +935,18 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
         return;
     }
 
-    // shared memory: keys[fast_cap] u64 | box_s[fast_cap] float4 | stage[fast_cap] u64 (later: kept keys, merge lists)
+    // shared memory: keys[fast_cap] u64 | box_s[fast_cap] float4 | kept_s[fast_cap] float4 | keep_bits
+    // (kept_s first holds the staged bucket, later the compacted kept keys; the merge reuses everything)
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(nms_smem);
     float4 *box_s = reinterpret_cast<float4 *>(nms_smem + (size_t)p.fast_cap * 8);
-    unsigned long long *stage = reinterpret_cast<unsigned long long *>(nms_smem + (size_t)p.fast_cap * 24);
-    unsigned *keep_bits = reinterpret_cast<unsigned *>(nms_smem + (size_t)p.fast_cap * 32);  // [fast_cap / 32 + 1]
+    float4 *kept_s = reinterpret_cast<float4 *>(nms_smem + (size_t)p.fast_cap * 24);
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(kept_s);
+    unsigned *keep_bits = reinterpret_cast<unsigned *>(nms_smem + (size_t)p.fast_cap * 40);  // [fast_cap / 32 + 1]
 
     const int n = ctr[g];
     const unsigned long long *bucket = p.ws.gkey + ((size_t)b * kGroups + g) * ((size_t)NT * kPpTile);
-    if (tid < kMaxClasses) g_cnt[tid] = 0;
-    if (tid < kMaxClasses) { x_minx[tid] = 0xffffffffu; x_miny[tid] = 0xffffffffu; }
-    if (tid == 0) { g_next = 0; g_fallback = 0; }
+    if (tid < kMaxClasses) { g_cnt[tid] = 0; g_fin[tid] = 0; x_minx[tid] = 0xffffffffu; x_miny[tid] = 0xffffffffu; }
+    if (tid == 0) { g_next = 0; g_next2 = 0; g_fallback = 0; g_nbig = 0; }
     for (int i = tid; i < (p.fast_cap >> 5) + 1; i += kNmsThreads) keep_bits[i] = 0u;
     __syncthreads();
     for (int i = tid; i < n; i += kNmsThreads) {
@@ -913,28 +988,38 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
             rank += (m > nc || (m == nc && o < c)) ? 1 : 0;
         }
         g_order[rank] = c;
+        if (nc > kTeamMin) atomicAdd(&g_nbig, 1);
     }
     __syncthreads();
     for (int i = tid; i < n; i += kNmsThreads) {
         const unsigned long long key = stage[i];
         keys[atomicAdd(&g_cursor[key_class(key)], 1)] = key;
     }
+    if (warp == 1) {  // sweep items: exclusive prefix of the chunk counts in class order
+        int c4[4], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { c4[u] = (g_cnt[g_order[lane * 4 + u]] + 31) >> 5; sum += c4[u]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        int run = inc - sum;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { g_cum[lane * 4 + u] = run; run += c4[u]; }
+        if (lane == 31) g_cum[kMaxClasses] = inc;
+    }
     __syncthreads();
     GPROF(2);
     const bool xcheck = use_off && xc > 0;
+    const int nbig = g_nbig;
 
-    // ---- one warp per class, largest first
-    for (;;) {
-        int oi = 0;
-        if (lane == 0) oi = atomicAdd(&g_next, 1);
-        oi = __shfl_sync(0xffffffffu, oi, 0);
-        if (oi >= kMaxClasses) break;
-        const int c = g_order[oi];
-        const int nc = g_cnt[c];
-        if (nc == 0) break;
-        const int s = g_begin[c];
-        warp_sort(keys + s, nc);
-        const float off = use_off ? (float)c * span : 0.f;  // tv:ops/boxes.py:100 (its own rounding)
+    // ---- sort + gather: class `oi` of the size order.  After the sort the boxes are fetched from L2 in
+    // sorted order, the exact cross-class check runs on the few boxes near the far corner, and the class
+    // offset is added (tv:ops/boxes.py:100-101, separate roundings).
+    auto gather_class = [&](const int c, const int s, const int nc, const int t0, const int tstride) {
+        const float off = use_off ? (float)c * span : 0.f;
         // A box of class c meets a cross box of a class k > c only if its x2 / y2 exceed
         // (min x1 / y1 of that class's cross boxes) + (k - c) * span (rounding: < 1): per-class limits.
         float lim_x = 3.0e38f, lim_y = 3.0e38f;
@@ -955,47 +1040,129 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
                 lim_y = fminf(lim_y, __shfl_xor_sync(0xffffffffu, lim_y, o));
             }
         }
-        for (int i0 = 0; i0 < nc; i0 += 128) {              // 4 independent gathers in flight per lane
+        for (int i0 = t0; i0 < nc; i0 += 4 * tstride) {  // 4 independent gathers in flight per thread
             float4 bx[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * 32 + lane;
+                const int i = i0 + u * tstride;
                 if (i < nc) bx[u] = p.ws.box[slot0 + key_slot(keys[s + i])];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * 32 + lane;
+                const int i = i0 + u * tstride;
                 if (i < nc) {
                     float4 y = bx[u];
-                    // exact cross-class check: only boxes within |min x1| x |min y1| of the far corner can be reached
-                    if (xcheck && y.z > lim_x && y.w > lim_y) {
+                    const bool near_corner = xcheck && y.z > lim_x && y.w > lim_y;
+                    y.x = y.x + off; y.y = y.y + off; y.z = y.z + off; y.w = y.w + off;
+                    box_s[s + i] = y;
+                    if (near_corner) {
                         const unsigned long long ky = keys[s + i];
-                        float4 yo = y;
-                        yo.x = yo.x + off; yo.y = yo.y + off; yo.z = yo.z + off; yo.w = yo.w + off;
                         for (int q = 0; q < xc; ++q) {
                             const unsigned long long kx = x_key[q];
                             if (key_class(kx) <= c) continue;  // the pair is found from the lower class's side
                             const float4 x = x_box[q];
-                            if (!(x.x < yo.z && x.y < yo.w && yo.x < x.z && yo.y < x.w)) continue;  // no overlap: quotient 0
+                            if (!(x.x < y.z && x.y < y.w && y.x < x.z && y.y < x.w)) continue;  // no overlap: quotient 0
                             const bool x_first = (kx & kOrderMask) < (ky & kOrderMask);
-                            if (x_first ? suppresses(x, yo, p.flavor, p.thr_f, p.thr_d) : suppresses(yo, x, p.flavor, p.thr_f, p.thr_d))
+                            if (x_first ? suppresses(x, y, p.flavor, p.thr_f, p.thr_d) : suppresses(y, x, p.flavor, p.thr_f, p.thr_d))
                                 g_fallback = 1;
                         }
                     }
-                    y.x = y.x + off; y.y = y.y + off; y.z = y.z + off; y.w = y.w + off;  // tv:ops/boxes.py:101
-                    box_s[s + i] = y;
                 }
             }
         }
+    };
+    {
+        const int team = warp >> 3, tw = warp & 7;
+        for (int oi = team; oi < nbig; oi += 4) {  // large classes: one team of 8 warps each
+            const int c = g_order[oi], nc = g_cnt[c], s = g_begin[c];
+            team_sort(keys + s, nc, tw, 1 + team);
+            gather_class(c, s, nc, tw * 32 + lane, 256);
+        }
+        for (;;) {  // the rest: one warp each, largest first
+            int oi = 0;
+            if (lane == 0) oi = nbig + atomicAdd(&g_next, 1);
+            oi = __shfl_sync(0xffffffffu, oi, 0);
+            if (oi >= kMaxClasses) break;
+            const int c = g_order[oi], nc = g_cnt[c];
+            if (nc == 0) break;
+            const int s = g_begin[c];
+            warp_sort(keys + s, nc);
+            gather_class(c, s, nc, lane, 32);
+        }
+    }
+    if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 8), (unsigned long long)clock64());
+    __syncthreads();
+
+    // ---- sweep: one item per chunk of 32 boxes, handed out in (class, chunk) order
+    const int n_items = g_cum[kMaxClasses];
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&g_next2, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        int lo = 0, hi = kMaxClasses;  // g_cum[lo] <= item < g_cum[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (g_cum[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int c = g_order[lo], s = g_begin[c], nc = g_cnt[c];
+        const int j = item - g_cum[lo], item0 = g_cum[lo];
+        const int i = s + 32 * j + lane;
+        const bool valid = 32 * j + lane < nc;
+        const float4 bx = valid ? box_s[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool dead = !valid;
+        int K = 0;
+        for (int jj = 0; jj < j; ++jj) {
+            while (g_fin[c] <= jj) __nanosleep(20);
+            __threadfence_block();  // the chunk's keeps (kept_s, g_kcum) were written before its flag
+            const int Knew = g_kcum[item0 + jj];
+            for (int k = K; k < Knew; k += 4) {
+                if (__all_sync(0xffffffffu, dead)) break;  // dense clusters die against the first keeps
+                // 4 independent tests per trip (entries past Knew: masked)
+                const float4 k0 = kept_s[s + k], k1 = kept_s[s + k + 1], k2 = kept_s[s + k + 2], k3 = kept_s[s + k + 3];
+                const bool s0 = suppresses(k0, bx, p.flavor, p.thr_f, p.thr_d);
+                const bool s1 = k + 1 < Knew && suppresses(k1, bx, p.flavor, p.thr_f, p.thr_d);
+                const bool s2 = k + 2 < Knew && suppresses(k2, bx, p.flavor, p.thr_f, p.thr_d);
+                const bool s3 = k + 3 < Knew && suppresses(k3, bx, p.flavor, p.thr_f, p.thr_d);
+                dead = dead || s0 || s1 || s2 || s3;
+            }
+            K = Knew;
+        }
+        // settle the chunk: lowest surviving lane == best remaining score: kept (stops at max_det keeps:
+        // later boxes of the class cannot reach the output)
+        unsigned alive = __ballot_sync(0xffffffffu, !dead);
+        unsigned keepm = 0u;
+        int room = p.max_det - K;
+        while (alive && room > 0) {
+            const int jl = __ffs(alive) - 1;
+            keepm |= 1u << jl;
+            alive &= ~(1u << jl);
+            --room;
+            if (!alive) break;
+            const float4 jb = make_float4(__shfl_sync(0xffffffffu, bx.x, jl), __shfl_sync(0xffffffffu, bx.y, jl),
+                                          __shfl_sync(0xffffffffu, bx.z, jl), __shfl_sync(0xffffffffu, bx.w, jl));
+            const bool sup = ((alive >> lane) & 1u) && suppresses(jb, bx, p.flavor, p.thr_f, p.thr_d);
+            alive &= ~__ballot_sync(0xffffffffu, sup);
+        }
+        if ((keepm >> lane) & 1u) kept_s[s + K + __popc(keepm & ((1u << lane) - 1u))] = bx;
+        if (lane == 0) {
+            if (keepm) {
+                const int c0 = s + 32 * j, w = c0 >> 5, sh = c0 & 31;
+                atomicOr(&keep_bits[w], keepm << sh);
+                if (sh && (keepm >> (32 - sh))) atomicOr(&keep_bits[w + 1], keepm >> (32 - sh));
+            }
+            g_kcum[item] = K + __popc(keepm);
+        }
+        __threadfence_block();
         __syncwarp();
-        warp_class_nms_inplace(box_s, keep_bits, s, s + nc, p.max_det, p.flavor, p.thr_f, p.thr_d);
+        if (lane == 0) g_fin[c] = j + 1;
     }
     if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 3), (unsigned long long)clock64());
     __syncthreads();
     if (tid == 0 && g_fallback) atomicOr(&ctr[kGroups + 3], 1);
 
-    // ---- kept keys of the group: class stripped, compacted, sorted, published
-    unsigned long long *keys2 = stage;
+    // ---- kept keys of the group: class stripped, compacted, sorted; the first max_det published as records
+    unsigned long long *keys2 = reinterpret_cast<unsigned long long *>(box_s);
     const int nwords = (n + 31) >> 5;
     if (warp == 0) {
         int c4[4], sum = 0;
@@ -1030,9 +1197,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
     GPROF(4);
     block_sort(keys2, n2);
     GPROF(5);
-    unsigned long long *pub = p.ws.kept + ((size_t)b * kGroups + g) * p.ws.kept_cap;
-    for (int i = tid; i < Kg; i += kNmsThreads) pub[i] = keys2[i];
-    if (tid == 0) p.ws.kcount[b * kGroups + g] = Kg;
+    const int Kpub = min(Kg, p.max_det);
+    KeptRec *pub = p.ws.krec + ((size_t)b * kGroups + g) * kRecCap;
+    for (int i = tid; i < Kpub; i += kNmsThreads) {
+        const unsigned long long key = keys2[i];
+        const int slot = key_slot(key);
+        KeptRec r;
+        r.key = key;
+        r.score = p.ws.score[slot0 + slot];
+        r.meta = p.ws.meta[slot0 + slot];
+        r.box = p.ws.box[slot0 + slot];
+        pub[i] = r;
+    }
+    if (tid == 0) p.ws.kcount[b * kGroups + g] = Kpub;
     __threadfence();
     __syncthreads();
     if (tid == 0) g_last = (atomicAdd(&ctr[kGroups + 2], 1) == kGroups - 1) ? 1 : 0;
@@ -1050,48 +1227,44 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
         if (prof && tid == 0) prof[14] = 1;
         return;
     }
-    // ---- merge: rank of a kept key = its position in its own list + the number of smaller keys in the others
-    unsigned long long *lists = reinterpret_cast<unsigned long long *>(nms_smem);  // up to kGroups * fast_cap keys (32 B each slot)
-    if (tid <= kGroups) {
-        int acc = 0;
-        for (int q = 0; q < tid; ++q) acc += __ldcg(&p.ws.kcount[b * kGroups + q]);
-        g_lcount[tid] = acc;  // exclusive prefix; [kGroups] = total
+    // ---- merge: every list is read blind (up to max_det records each) together with the counts; the rank
+    // of a kept key = its position in its own list + the number of smaller keys in the other lists
+    KeptRec *recs = reinterpret_cast<KeptRec *>(nms_smem);  // [kGroups][max_det]
+    if (tid < kGroups) g_lcount[tid] = __ldcg(&p.ws.kcount[b * kGroups + tid]);
+    for (int e = tid; e < kGroups * p.max_det; e += kNmsThreads) {
+        const int q = e / p.max_det, i = e - q * p.max_det;
+        const float4 *src = reinterpret_cast<const float4 *>(p.ws.krec + ((size_t)b * kGroups + q) * kRecCap + i);
+        float4 *dst = reinterpret_cast<float4 *>(recs + e);
+        dst[0] = __ldcg(src);
+        dst[1] = __ldcg(src + 1);
     }
     __syncthreads();
-    const int Kt = g_lcount[kGroups];
-    for (int q = 0; q < kGroups; ++q) {
-        const unsigned long long *src = p.ws.kept + ((size_t)b * kGroups + q) * p.ws.kept_cap;
-        const int lo = g_lcount[q], cnt = g_lcount[q + 1] - lo;
-        for (int i = tid; i < cnt; i += kNmsThreads) lists[lo + i] = __ldcg(src + i);
-    }
-    __syncthreads();
-    const int nkept = min(Kt, p.max_det);
-    for (int e = tid; e < Kt; e += kNmsThreads) {
-        int q = 0;
+    int Kt = 0;
 #pragma unroll
-        for (int u = 1; u < kGroups; ++u) q += (e >= g_lcount[u]) ? 1 : 0;
-        const unsigned long long key = lists[e];
-        int rank = e - g_lcount[q];
+    for (int q = 0; q < kGroups; ++q) Kt += g_lcount[q];
+    const int nkept = min(Kt, p.max_det);
+    for (int e = tid; e < kGroups * p.max_det; e += kNmsThreads) {
+        const int q = e / p.max_det, i = e - q * p.max_det;
+        if (i >= g_lcount[q]) continue;
+        const KeptRec r = recs[e];
+        int rank = i;
 #pragma unroll
         for (int u = 0; u < kGroups; ++u) {
             if (u == q) continue;
-            int lo = g_lcount[u], hi = g_lcount[u + 1];  // first position with key' > key (keys are distinct)
-            const int base = lo;
+            int lo = 0, hi = g_lcount[u];  // first position with key' > key (keys are distinct)
+            const KeptRec *lst = recs + u * p.max_det;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (lists[mid] < key) lo = mid + 1; else hi = mid;
+                if (lst[mid].key < r.key) lo = mid + 1; else hi = mid;
             }
-            rank += lo - base;
+            rank += lo;
         }
         if (rank < nkept) {
-            const int slot = key_slot(key);
-            const float4 bx = p.ws.box[slot0 + slot];
-            const int meta = p.ws.meta[slot0 + slot];
             float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + rank) * 6);
-            d[0] = make_float2(bx.x, bx.y);
-            d[1] = make_float2(bx.z, bx.w);
-            d[2] = make_float2(p.ws.score[slot0 + slot], (float)(meta >> 24));
-            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = meta & 0xffffff;
+            d[0] = make_float2(r.box.x, r.box.y);
+            d[1] = make_float2(r.box.z, r.box.w);
+            d[2] = make_float2(r.score, (float)(r.meta >> 24));
+            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = r.meta & 0xffffff;
         }
     }
     for (int i = nkept + tid; i < p.max_det; i += kNmsThreads) {

@@ -27,6 +27,15 @@ constexpr int kMaxCross = 512;  // boxes that may reach into another class's off
 constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
 constexpr int kImgCtr = 8;      // ints per image in the counter block (zeroed before every call)
 
+constexpr int kRecCap = 1024;   // >= max_det: a group contributes at most max_det rows to the image's output
+
+struct __align__(16) KeptRec {  // one kept box as the merge needs it
+    unsigned long long key;     // ~ordered(score) << 25 | slot: the global order
+    float score;
+    int meta;                   // anchor | class << 24
+    float4 box;
+};
+
 struct CandWs {
     int *tile_count;    // [B, NT]
     float4 *box;        // [B, NT*128]  original (un-offset) corners
@@ -37,9 +46,8 @@ struct CandWs {
     unsigned long long *gkey;     // [B, kGroups, NT*128]  class << 57 | ~ordered(score) << 25 | slot
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
-    unsigned long long *kept;     // [B, kGroups, kept_cap] kept keys of every group, sorted, class stripped
+    KeptRec *krec;                // [B, kGroups, kRecCap] first kept boxes of every group, global order
     int *kcount;                  // [B, kGroups]
-    int kept_cap;
 };
 
 struct ScoreParams {
@@ -280,7 +288,6 @@ static thread_local long long *g_nms_prof = nullptr;
 static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t off = 0;
     const size_t slots = (size_t)B * NT * kPpTile;
-    const int kept_cap = NT * kPpTile < kFastCap ? NT * kPpTile : kFastCap;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     size_t o_ctr = take((size_t)B * kImgCtr * sizeof(int));  // first: zeroed before every call
     size_t o_cnt = take((size_t)B * NT * sizeof(int));
@@ -290,7 +297,7 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t o_gkey = take(slots * kGroups * sizeof(unsigned long long));
     size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
     size_t o_xbox = take((size_t)B * kMaxCross * sizeof(float4));
-    size_t o_kept = take((size_t)B * kGroups * kept_cap * sizeof(unsigned long long));
+    size_t o_kept = take((size_t)B * kGroups * kRecCap * sizeof(KeptRec));
     size_t o_kcnt = take((size_t)B * kGroups * sizeof(int));
     if (ws) {
         ws->ctr = reinterpret_cast<int *>(base + o_ctr);
@@ -301,9 +308,8 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
         ws->gkey = reinterpret_cast<unsigned long long *>(base + o_gkey);
         ws->xkey = reinterpret_cast<unsigned long long *>(base + o_xkey);
         ws->xbox = reinterpret_cast<float4 *>(base + o_xbox);
-        ws->kept = reinterpret_cast<unsigned long long *>(base + o_kept);
+        ws->krec = reinterpret_cast<KeptRec *>(base + o_kept);
         ws->kcount = reinterpret_cast<int *>(base + o_kcnt);
-        ws->kept_cap = kept_cap;
     }
     return off;
 }
@@ -324,8 +330,8 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     np.fast_cap = cap < kFastCap ? cap : kFastCap;
     np.ws = ws; np.dets = dets; np.counts = counts; np.keep_idx = keep_idx;
     np.prof = g_nms_prof;
-    const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
-    PLYOLO_REQUIRE(smem <= 208 * 1024, "nms working set (%zu B) exceeds shared memory", smem);
+    const size_t smem = nms_group_smem_bytes(cap, np.fast_cap, max_det, NT);
+    PLYOLO_REQUIRE(smem <= 190 * 1024, "nms working set (%zu B) exceeds shared memory", smem);
     cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     nms_group_kernel<<<dim3(kGroups, B), kNmsThreads, smem, stream>>>(np);
     PLYOLO_CHECK_LAUNCH("nms_group_kernel");
