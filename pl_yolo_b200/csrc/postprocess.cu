@@ -59,145 +59,133 @@ struct ScoreParams {
     CandWs ws;
 };
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
-    extern __shared__ __align__(128) float tile[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int warp_cnt[kPpTile / 32];
+// per consumer group (128 threads = one tile at a time) scratch
+struct TileShared {
+    int warp_cnt[kPpTile / 32];
+    int g_wcnt[kPpTile / 32][kGroups];
+    int g_base[kGroups];
+    float w_max[kPpTile / 32];
+};
 
-    const int b = blockIdx.y;
-    const int tile_id = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int ch = p.ch;
-    int l = 0, a0, cnt, anchor_base;
-    const float *src;
+struct TileCoord {
+    int b, tile_id, l, a0, cnt, anchor_base;
+    const float *src;  // FUSED: first anchor of channel 0 of the tile; else first row of the tile in preds
+};
+
+template <bool FUSED>
+__device__ __forceinline__ TileCoord tile_coord(const ScoreParams &p, const int b, const int tile_id) {
+    TileCoord t;
+    t.b = b; t.tile_id = tile_id; t.l = 0;
     if (FUSED) {
 #pragma unroll
         for (int i = 1; i < PLYOLO_MAX_LEVELS; ++i)
-            if (i < p.lv.n && tile_id >= p.lv.tile0[i]) l = i;
-        a0 = (tile_id - p.lv.tile0[l]) * kPpTile;
-        cnt = min(kPpTile, p.lv.hw[l] - a0);
-        anchor_base = p.lv.off[l] + a0;
-        src = p.lv.ptr[l] + (size_t)b * ch * p.lv.hw[l] + a0;
+            if (i < p.lv.n && tile_id >= p.lv.tile0[i]) t.l = i;
+        t.a0 = (tile_id - p.lv.tile0[t.l]) * kPpTile;
+        t.cnt = min(kPpTile, p.lv.hw[t.l] - t.a0);
+        t.anchor_base = p.lv.off[t.l] + t.a0;
+        t.src = p.lv.ptr[t.l] + (size_t)b * p.ch * p.lv.hw[t.l] + t.a0;
     } else {
-        a0 = tile_id * kPpTile;
-        cnt = min(kPpTile, p.A - a0);
-        anchor_base = a0;
-        src = p.preds + ((size_t)b * p.A + a0) * ch;
+        t.a0 = tile_id * kPpTile;
+        t.cnt = min(kPpTile, p.A - t.a0);
+        t.anchor_base = t.a0;
+        t.src = p.preds + ((size_t)b * p.A + t.a0) * p.ch;
     }
+    return t;
+}
 
-    // ---- stage the tile in shared memory
-    if (p.bulk_ok) {
-        if (tid == 0) {
-            mbar_init(&bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (FUSED) {
-            if (tid < 32) {
-                if (tid == 0) mbar_expect_tx(&bar, (uint32_t)(ch * cnt * 4));
-                __syncwarp();
-                for (int c = tid; c < ch; c += 32)
-                    bulk_g2s(tile + c * kPpTile, src + (size_t)c * p.lv.hw[l], (uint32_t)(cnt * 4), &bar);
-            }
-        } else if (tid == 0) {
-            mbar_expect_tx(&bar, (uint32_t)(cnt * ch * 4));
-            bulk_g2s(tile, src, (uint32_t)(cnt * ch * 4), &bar);
-        }
-        mbar_wait(&bar, 0);
-    } else {
-        if (FUSED) {
-            for (int c = 0; c < ch; ++c)
-                if (tid < cnt) tile[c * kPpTile + tid] = __ldg(src + (size_t)c * p.lv.hw[l] + tid);
-        } else {
-            for (int i = tid; i < cnt * ch; i += kPpTile) tile[i] = __ldg(src + i);
-        }
-        __syncthreads();
-    }
+__device__ __forceinline__ void group_barrier(const int bar_id) {
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+}
 
+// Scores one staged tile (128 threads, `tid` in [0,128), barrier `bar_id`).  `tile` is read-only here; after
+// the call returns the group no longer needs it IF `release` was invoked (it is called once, by every thread,
+// right after the last read of the tile).
+template <bool FUSED, typename Release>
+__device__ __forceinline__ void score_tile(const ScoreParams &p, const float *tile, const TileCoord tc, const int tid,
+                                           const int bar_id, TileShared &sh, Release release) {
+    const int ch = p.ch, b = tc.b, l = tc.l, a0 = tc.a0, cnt = tc.cnt;
     const int lane = tid & 31, warp = tid >> 5;
     bool pass = false;
     float conf = 0.f;
     int cls = 0;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    int src_t = tid;  // tile-local anchor this thread finally reports
+    const int src_t = tid;  // tile-local anchor of this thread
 
     if (FUSED) {
-        // ---- pass A (one thread per anchor): sigmoid(obj), max raw class logit, conservative pre-filter.
-        // conf = fl(so * max_c sigmoid(x_c)).  sigmoid is monotone up to a few ulp, so with m = max_c x_c:
-        // conf <= so * sigmoid(m) * (1 + 1e-6); anchors with fl(fl(so * sigmoid(m)) * 1.00001f) < thr cannot pass.
-        // Survivors (exactness restored in pass B) are compacted in anchor order.
-        __shared__ unsigned char surv[kPpTile];
-        __shared__ float s_so[kPpTile];
-        __shared__ float s_best[kPpTile];
-        __shared__ int s_cls[kPpTile];
-        bool pre = false;
-        float so = 0.f;
+        // One thread per anchor.  conf = fl(sigmoid(obj) * max_c sigmoid(x_c)) and the FIRST class attaining the
+        // max over the sigmoid VALUES (postprocess.py:18 works on the already-squashed tensor; T1).
+        //  1. so = sigmoid(obj); so < thr cannot pass (class_conf <= 1, fp32 multiply is monotone);
+        //  2. m = max raw logit (4 independent chains); conservative pre-filter on fl(so * sigmoid(m)) * 1.00001;
+        //  3. exact argmax: the fp32 sigmoid is monotone only up to rounding (relative error < 4e-7), so every
+        //     class whose logit is >= t can still tie with or beat sigmoid(m), where
+        //     t = -log(e^-m + 2e-6 (1 + e^-m)) - margin  (i.e. sigmoid(t) = sigmoid(m) (1 - 2e-6) with slack);
+        //     only those (normally just the arg max; many when the logits saturate) are evaluated exactly.
         if (tid < cnt) {
-            so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
-            if (so >= p.conf_thr) {                     // class_conf <= 1 and fp32 multiply is monotone
-                float m = tile[5 * kPpTile + tid];
-                for (int c = 1; c < p.C; ++c) m = fmaxf(m, tile[(5 + c) * kPpTile + tid]);
-                pre = (so * sigmoid_ref(m)) * 1.00001f >= p.conf_thr;
-            }
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, pre);
-        if (lane == 0) warp_cnt[warp] = __popc(pm);
-        __syncthreads();
-        int sbase = 0, nsurv = 0;
+            const float so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
+            if (so >= p.conf_thr) {
+                // one branch-free sweep, 4 independent chains (classes = chain mod 4): largest and second largest
+                // raw logit and the first index of the largest
+                const float *col = tile + 5 * kPpTile + tid;
+                float m1[4], m2[4];
+                int i1[4];
 #pragma unroll
-        for (int w = 0; w < kPpTile / 32; ++w) {
-            if (w < warp) sbase += warp_cnt[w];
-            nsurv += warp_cnt[w];
-        }
-        if (pre) {
-            const int si = sbase + __popc(pm & ((1u << lane) - 1u));
-            surv[si] = (unsigned char)tid;
-            s_so[si] = so;
-        }
-        __syncthreads();
-        // ---- pass B: 4 lanes per survivor, each takes a quarter of the classes: exact max / first argmax
-        // over the sigmoid VALUES (postprocess.py:18 works on the already-squashed tensor; T1)
-        const int cq = (p.C + 3) >> 2;
-        for (int it = 0; it * (kPpTile >> 2) < nsurv; ++it) {
-            const int si = it * (kPpTile >> 2) + (tid >> 2), q = tid & 3;
-            float best = -1.f;
-            int bi = 0x7fffffff;
-            if (si < nsurv) {
-                const int t = surv[si];
-                const int c0 = q * cq, c1 = min(p.C, c0 + cq);
-                for (int c = c0; c < c1; ++c) {
-                    const float v = sigmoid_ref(tile[(5 + c) * kPpTile + t]);  // yolox_loss.py:27
-                    if (v > best) { best = v; bi = c; }
+                for (int u = 0; u < 4; ++u) { m1[u] = -3.0e38f; m2[u] = -3.0e38f; i1[u] = 0; }
+                int c = 0;
+                for (; c + 3 < p.C; c += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float x = col[(c + u) * kPpTile];
+                        m2[u] = fmaxf(m2[u], fminf(x, m1[u]));
+                        i1[u] = x > m1[u] ? c + u : i1[u];
+                        m1[u] = fmaxf(m1[u], x);
+                    }
+                }
+                for (; c < p.C; ++c) {
+                    const float x = col[c * kPpTile];
+                    m2[0] = fmaxf(m2[0], fminf(x, m1[0]));
+                    i1[0] = x > m1[0] ? c : i1[0];
+                    m1[0] = fmaxf(m1[0], x);
+                }
+#pragma unroll
+                for (int u = 1; u < 4; ++u) {  // fold chain u into chain 0
+                    m2[0] = fmaxf(fmaxf(m2[0], m2[u]), fminf(m1[0], m1[u]));
+                    i1[0] = m1[u] > m1[0] ? i1[u] : (m1[u] == m1[0] ? min(i1[0], i1[u]) : i1[0]);
+                    m1[0] = fmaxf(m1[0], m1[u]);
+                }
+                const float m = m1[0];
+                const float sm = sigmoid_ref(m);  // yolox_loss.py:27
+                if ((so * sm) * 1.00001f >= p.conf_thr) {
+                    const float em = expf(-m);
+                    float t = -logf(em + 2.0e-6f * (1.0f + em));
+                    t = t - 1.0e-5f * (1.0f + fabsf(t));
+                    if (!(t <= m)) t = m;  // NaN / overflow guard: at least the max itself is evaluated
+                    float best = sm;
+                    cls = i1[0];
+                    if (m2[0] >= t) {  // rare: several logits inside the window (saturation, near ties): exact sweep
+                        best = -1.f;
+                        for (int cc = 0; cc < p.C; ++cc) {
+                            const float x = col[cc * kPpTile];
+                            if (x >= t) {
+                                const float v = sigmoid_ref(x);
+                                if (v > best) { best = v; cls = cc; }
+                            }
+                        }
+                    }
+                    conf = so * best;           // postprocess.py:19
+                    pass = conf >= p.conf_thr;  // :20 (fp32 compare)
+                    if (pass) {
+                        const int a = a0 + tid;
+                        const int W = p.lv.w[l];
+                        const float s = p.lv.stride[l];
+                        const float cx = (tile[0 * kPpTile + tid] + (float)(a % W)) * s;  // yolox_loss.py:217
+                        const float cy = (tile[1 * kPpTile + tid] + (float)(a / W)) * s;
+                        const float w = expf(tile[2 * kPpTile + tid]) * s;                // :219
+                        const float h = expf(tile[3 * kPpTile + tid]) * s;
+                        box = make_float4(cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2);  // :31-34
+                    }
                 }
             }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (si < nsurv && q == 0) { s_best[si] = best; s_cls[si] = bi; }
         }
-        __syncthreads();
-        // ---- final filter + box decode, one thread per survivor (still anchor order)
-        if (tid < nsurv) {
-            src_t = surv[tid];
-            cls = s_cls[tid];
-            conf = s_so[tid] * s_best[tid];    // postprocess.py:19
-            pass = conf >= p.conf_thr;         // :20 (fp32 compare)
-            if (pass) {
-                const int a = a0 + src_t;
-                const int W = p.lv.w[l];
-                const float s = p.lv.stride[l];
-                const float cx = (tile[0 * kPpTile + src_t] + (float)(a % W)) * s;  // yolox_loss.py:217
-                const float cy = (tile[1 * kPpTile + src_t] + (float)(a / W)) * s;
-                const float w = expf(tile[2 * kPpTile + src_t]) * s;                // :219
-                const float h = expf(tile[3 * kPpTile + src_t]) * s;
-                box = make_float4(cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2);  // :31-34
-            }
-        }
-        __syncthreads();  // warp_cnt is reused below
     } else if (tid < cnt) {
         const float *r = tile + tid * ch;
         float best = r[5];
@@ -209,61 +197,59 @@ __global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
         pass = conf >= p.conf_thr;
         box = make_float4(r[0], r[1], r[2], r[3]);
     }
+    release();  // last read of the tile is done (every thread calls it)
 
     // ---- order-preserving compaction into the tile's slots (postprocess.py:23 keeps anchor order)
     const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kPpTile / 32; ++w) {
-        if (w < warp) base += warp_cnt[w];
-        total += warp_cnt[w];
-    }
-    const int islot = tile_id * kPpTile + base + __popc(m & ((1u << lane) - 1u));  // slot inside the image
-    if (pass) {
-        const size_t slot = (size_t)b * p.NT * kPpTile + islot;
-        p.ws.box[slot] = box;
-        p.ws.score[slot] = conf;
-        p.ws.meta[slot] = (anchor_base + src_t) | (cls << 24);
-    }
-    if (tid == 0) p.ws.tile_count[b * p.NT + tile_id] = total;
-
-    // ---- class-group buckets for the NMS stage (one CTA per image and group): keys in arrival order, the
-    // image's max coordinate (tv:ops/boxes.py:99) and the boxes that can reach another class's offset range
-    if (total == 0) return;
-    __shared__ int g_wcnt[kPpTile / 32][kGroups];
-    __shared__ int g_base[kGroups];
-    __shared__ float w_max[kPpTile / 32];
+    if (lane == 0) sh.warp_cnt[warp] = __popc(m);
+    // class-group ballots and the tile's max coordinate ride on the same barrier
     const int grp = cls & (kGroups - 1);
     unsigned gm = 0u;
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
         const unsigned mg = __ballot_sync(0xffffffffu, pass && grp == g);
-        if (lane == 0) g_wcnt[warp][g] = __popc(mg);
+        if (lane == 0) sh.g_wcnt[warp][g] = __popc(mg);
         if (grp == g) gm = mg;
     }
     float cm = pass ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -3.0e38f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-    if (lane == 0) w_max[warp] = cm;
-    __syncthreads();
+    if (lane == 0) sh.w_max[warp] = cm;
+    group_barrier(bar_id);
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kPpTile / 32; ++w) {
+        if (w < warp) base += sh.warp_cnt[w];
+        total += sh.warp_cnt[w];
+    }
+    const int islot = tc.tile_id * kPpTile + base + __popc(m & ((1u << lane) - 1u));  // slot inside the image
+    if (pass) {
+        const size_t slot = (size_t)b * p.NT * kPpTile + islot;
+        p.ws.box[slot] = box;
+        p.ws.score[slot] = conf;
+        p.ws.meta[slot] = (tc.anchor_base + src_t) | (cls << 24);
+    }
+    if (tid == 0) p.ws.tile_count[b * p.NT + tc.tile_id] = total;
+
+    // ---- class-group buckets for the NMS stage (one CTA per image and group): keys in arrival order, the
+    // image's max coordinate (tv:ops/boxes.py:99) and the boxes that can reach another class's offset range
+    if (total == 0) return;  // uniform for the group
     int *ctr = p.ws.ctr + b * kImgCtr;
     if (tid < kGroups) {
         int n = 0;
 #pragma unroll
-        for (int w = 0; w < kPpTile / 32; ++w) n += g_wcnt[w][tid];
-        g_base[tid] = n ? atomicAdd(&ctr[tid], n) : 0;
+        for (int w = 0; w < kPpTile / 32; ++w) n += sh.g_wcnt[w][tid];
+        sh.g_base[tid] = n ? atomicAdd(&ctr[tid], n) : 0;
     } else if (tid == 32) {
-        float mx = w_max[0];
+        float mx = sh.w_max[0];
 #pragma unroll
-        for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, w_max[w]);
+        for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, sh.w_max[w]);
         atomicMax(reinterpret_cast<unsigned *>(&ctr[kGroups]), float_ordered(mx));
     }
-    __syncthreads();
+    group_barrier(bar_id);
     if (pass) {
-        int pos = g_base[grp] + __popc(gm & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) pos += g_wcnt[w][grp];
+        int pos = sh.g_base[grp] + __popc(gm & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) pos += sh.g_wcnt[w][grp];
         const unsigned long long key = ((unsigned long long)cls << 57) |
                                        ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)islot;
         p.ws.gkey[((size_t)b * kGroups + grp) * ((size_t)p.NT * kPpTile) + pos] = key;
@@ -273,6 +259,104 @@ __global__ void __launch_bounds__(kPpTile) score_kernel(const ScoreParams p) {
                 p.ws.xkey[(size_t)b * kMaxCross + xi] = key;
                 p.ws.xbox[(size_t)b * kMaxCross + xi] = box;
             }
+        }
+    }
+}
+
+// ---- one CTA per tile, plain loads: the fallback for unaligned inputs (no 16-byte alignment for bulk copies)
+template <bool FUSED>
+__global__ void __launch_bounds__(kPpTile) score_kernel_simple(const ScoreParams p) {
+    extern __shared__ __align__(128) float tile[];
+    __shared__ TileShared sh;
+    const int tid = threadIdx.x;
+    const TileCoord tc = tile_coord<FUSED>(p, blockIdx.y, blockIdx.x);
+    if (FUSED) {
+        for (int c = 0; c < p.ch; ++c)
+            if (tid < tc.cnt) tile[c * kPpTile + tid] = __ldg(tc.src + (size_t)c * p.lv.hw[tc.l] + tid);
+    } else {
+        for (int i = tid; i < tc.cnt * p.ch; i += kPpTile) tile[i] = __ldg(tc.src + i);
+    }
+    __syncthreads();
+    score_tile<FUSED>(p, tile, tc, tid, 0, sh, [] {});
+}
+
+// ---- persistent, TMA-pipelined score kernel ---------------------------------------------------------
+// One CTA per SM walks the (image, tile) list with stride gridDim.x.  Warp 0 is the producer: for every
+// tile it waits for a free stage and copies the tile asynchronously onto the stage's mbarrier — from the
+// channel-planar head maps with 16-byte cp.async (one 512 B row per warp instruction: the TMA engine's
+// per-request service time caps 512 B bulk copies near 3 TB/s chip-wide, measured), from preds with one
+// contiguous TMA bulk copy of the whole tile.  Three consumer
+// groups of 128 threads take the tiles round-robin, so the scoring latency of one tile (dependent max
+// chains, barriers, the bucket atomics) overlaps the next tiles' loads and compute.
+constexpr int kStages = 4;
+constexpr int kConsumers = 3;
+constexpr int kScoreThreads = 32 + kPpTile * kConsumers;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only) and its completion hook: the mbarrier
+// receives one (pre-counted) arrival from this thread once all of its earlier cp.async have landed
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kScoreThreads, 1) score_kernel(const ScoreParams p) {
+    extern __shared__ __align__(128) float stages[];  // [kStages][ch * 128]
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ TileShared sh[kConsumers];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stage_floats = p.ch * kPpTile;
+    const int total = p.NT * p.B;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], FUSED ? 32 : 1); mbar_init(&empty_bar[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // ---- producer
+        int seq = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++seq) {
+            const int s = seq % kStages, k = seq / kStages;
+            if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
+            const TileCoord tc = tile_coord<FUSED>(p, t / p.NT, t % p.NT);
+            float *dst = stages + (size_t)s * stage_floats;
+            if (FUSED) {
+                if (lane * 4 < tc.cnt) {  // cnt is a multiple of 4 (bulk_ok)
+                    const float *g = tc.src + lane * 4;
+                    float *d = dst + lane * 4;
+                    const size_t hw = (size_t)p.lv.hw[tc.l];
+#pragma unroll 5
+                    for (int c = 0; c < p.ch; ++c) cp_async16(d + c * kPpTile, g + c * hw);
+                }
+                cp_async_arrive(&full_bar[s]);
+            } else if (lane == 0) {
+                mbar_expect_tx(&full_bar[s], (uint32_t)(p.ch * tc.cnt * 4));
+                bulk_g2s(dst, tc.src, (uint32_t)(tc.cnt * p.ch * 4), &full_bar[s]);
+            }
+        }
+    } else {
+        // ---- consumers
+        const int grp = (warp - 1) >> 2, gtid = tid - 32 - grp * kPpTile;
+        for (int seq = grp;; seq += kConsumers) {
+            const int t = blockIdx.x + seq * gridDim.x;
+            if (t >= total) break;
+            const int s = seq % kStages, k = seq / kStages;
+            // Stage s is consumed by a different group every time (3 groups, 4 stages), and an mbarrier wait only
+            // knows the phase PARITY: waiting for fill k while fill k-1 has not even landed would return at
+            // once.  The stage's release k-1 (which implies fill k-1 completed and was consumed; release k-2 is
+            // already implied by this group's own progress) is therefore awaited first.
+            if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
+            mbar_wait(&full_bar[s], k & 1);
+            const TileCoord tc = tile_coord<FUSED>(p, t / p.NT, t % p.NT);
+            score_tile<FUSED>(p, stages + (size_t)s * stage_floats, tc, gtid, 1 + grp, sh[grp], [&] {
+                group_barrier(1 + grp);
+                if (gtid == 0) mbar_arrive(&empty_bar[s]);
+            });
         }
     }
 }
@@ -338,6 +422,38 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     return PLYOLO_OK;
 }
 
+static int sm_count() {
+    static thread_local int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// zeroes the per-image counters, then scores every tile (persistent TMA pipeline; plain-load kernel if unaligned)
+template <bool FUSED>
+static int launch_score(const ScoreParams &sp, cudaStream_t stream) {
+    if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)sp.B * kImgCtr * sizeof(int), stream) != cudaSuccess) {
+        set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+        return PLYOLO_ERR_CUDA;
+    }
+    const size_t tile_b = (size_t)kPpTile * sp.ch * sizeof(float);
+    if (sp.bulk_ok) {
+        const size_t smem = tile_b * kStages;
+        cudaFuncSetAttribute(score_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int total = sp.NT * sp.B, sms = sm_count();
+        score_kernel<FUSED><<<total < sms ? total : sms, kScoreThreads, smem, stream>>>(sp);
+        PLYOLO_CHECK_LAUNCH("score_kernel");
+    } else {
+        if (tile_b > 48 * 1024) cudaFuncSetAttribute(score_kernel_simple<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_b);
+        score_kernel_simple<FUSED><<<dim3(sp.NT, sp.B), kPpTile, tile_b, stream>>>(sp);
+        PLYOLO_CHECK_LAUNCH("score_kernel_simple");
+    }
+    return PLYOLO_OK;
+}
+
 static int check_post_args(int B, int A, int C, int max_nms, int max_det, int flavor, float *dets, int32_t *counts,
                            void *workspace, size_t workspace_bytes) {
     PLYOLO_REQUIRE(B >= 1 && B <= 65535, "B=%d not in [1,65535]", B);
@@ -384,14 +500,8 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (A & 3) == 0) ? 1 : 0;
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
-    const size_t smem = (size_t)kPpTile * sp.ch * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)B * kImgCtr * sizeof(int), (cudaStream_t)stream) != cudaSuccess) {
-        set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
-        return PLYOLO_ERR_CUDA;
-    }
-    score_kernel<false><<<dim3(sp.NT, B), kPpTile, smem, (cudaStream_t)stream>>>(sp);
-    PLYOLO_CHECK_LAUNCH("score_kernel<preds>");
+    rc = launch_score<false>(sp, (cudaStream_t)stream);
+    if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
                    (cudaStream_t)stream);
 }
@@ -417,14 +527,8 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     for (int l = 0; l < sp.lv.n; ++l) bulk = bulk && ((uintptr_t)sp.lv.ptr[l] & 15) == 0 && (sp.lv.hw[l] & 3) == 0;
     sp.bulk_ok = bulk ? 1 : 0;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
-    const size_t smem = (size_t)kPpTile * sp.ch * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)B * kImgCtr * sizeof(int), (cudaStream_t)stream) != cudaSuccess) {
-        set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
-        return PLYOLO_ERR_CUDA;
-    }
-    score_kernel<true><<<dim3(sp.NT, B), kPpTile, smem, (cudaStream_t)stream>>>(sp);
-    PLYOLO_CHECK_LAUNCH("score_kernel<fused>");
+    rc = launch_score<true>(sp, (cudaStream_t)stream);
+    if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
                    (cudaStream_t)stream);
 }

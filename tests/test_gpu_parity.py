@@ -168,6 +168,32 @@ def test_fused_decode_postprocess(B, size, seed, mode):
     assert (np.abs(o["counts"] - rc) <= 2).all()
 
 
+def test_fused_argmax_saturation_and_near_ties():
+    """Argmax is taken over the sigmoid VALUES (postprocess.py:18): saturated logits tie at 1.0 and the
+    first class wins, logits a few ulp apart may round to the same or even an inverted sigmoid.  The fused kernel
+    evaluates only a window of classes around the max logit exactly; it must agree with decode -> postprocess and
+    with the reference's op chain on CUDA for adversarial class logits."""
+    rng = np.random.default_rng(77)
+    B, size = 2, 320
+    heads = synth.make_heads(B, size, 80, 35, mode="clustered")
+    for h in heads:
+        n = h[:, 5:].size
+        shape = h[:, 5:].shape
+        pick = rng.choice([-40.0, -20.0, -3.0, 0.0, 2.0, 9.0, 13.0, 16.0, 16.5, 16.9, 17.0, 17.3, 17.33, 18.0, 20.0, 40.0, 88.0], n).reshape(shape)
+        jitter = rng.choice([0.0, 0.0, 1e-7, -1e-7, 1e-6, 3e-6, -2e-6, 1e-5], n).reshape(shape)
+        mask = rng.uniform(0, 1, shape) < 0.5
+        h[:, 5:] = np.where(mask, (pick * (1.0 + jitter)).astype(np.float32), h[:, 5:])
+        h[:, 4] = rng.normal(0.0, 3.0, h[:, 4].shape)  # many anchors pass the objectness gate
+    hd = [cu(h) for h in heads]
+    for conf in (0.01, 0.5, 0.999):
+        preds, _ = ops.decode_raw(hd, STRIDES, True)
+        d1, c1, k1 = ops.postprocess_raw(preds, conf, 0.65, False, 10000, 300, 0)
+        d2, c2, k2 = ops.decode_postprocess_raw(hd, STRIDES, conf, 0.65, False, 10000, 300, 0)
+        assert torch.equal(c1, c2) and torch.equal(k1, k2) and torch.equal(d1, d2), "fused path differs from decode->postprocess"
+        rd, rc = replay_dets(R.decode(hd, STRIDES, True)[0], conf, 0.65, False)
+        assert np.array_equal(c2.cpu().numpy(), rc) and np.array_equal(d2.cpu().numpy(), rd)
+
+
 def test_postprocess_cfg2_properties():
     """BASELINE cfg2 at full size (B=32, 640^2): size-independent properties + CUDA-replay equality."""
     B = 32
