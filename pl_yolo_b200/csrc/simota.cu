@@ -1,28 +1,27 @@
 // simota.cu — SimOTA label assignment for a whole batch (yolox_loss.py:43-118, :231-370;
-// iou_loss.py:391-414).  Three launches, no host synchronisation, no [G,Nc,80] temporaries.
+// iou_loss.py:391-414).  Two launches, no host synchronisation, no [G,Nc,80] temporaries.
 //
-//  K1 simota_prep_kernel      one CTA per image
+//  K1 simota_prep_kernel      4 CTAs per image
 //     GT count (:43), closed-form geometry prior: for every (GT, level) the in-box and in-centre
 //     anchors are axis-aligned cell rectangles, found with the reference's own fp32 comparisons
-//     (edge rounded first, then the delta, :249-307) and rasterised into shared-memory bitmaps:
-//     fg = union of all rectangles (:310), U = union of the (in-box AND in-centre) rectangles.
-//     Both bitmaps are compacted in anchor order; the candidates' corner boxes and areas are gathered
+//     (edge rounded first, then the delta, :249-307) and rasterised into a shared-memory bitmap
+//     fg = union of all rectangles (:310).  Every CTA builds the whole bitmap (cheap) and takes a
+//     quarter of the anchors: background defaults of the outputs, ordered compaction of the
+//     candidates (candidate n <-> n-th set bit, :79-82) and the gather of their corner boxes / areas
 //     (16 of the 340 bytes of each prediction row) for the IoU sweep.
-//  K2 simota_cost_table_kernel  one warp per anchor of U
-//     the 80-class BCE cost of the anchor for EVERY possible GT class from one reduction in ATen's
-//     CUDA order (measured on B200: lane t adds classes t, t+32, t+64, then a halving tree): a
-//     butterfly over the all-negative leaves leaves each lane the sibling sums of its path, and
-//     swapping in the positive leaf re-adds them.  O(|U|*C) transcendentals instead of O(G*Nc*C).
-//  K3 simota_match_kernel     one CTA (4 warps) per GT
-//     IoU against every candidate with warp-resident top-10 lists (values only, :336-340; the
-//     division runs only when a pair can enter the list) -> dynamic k with ATen's reduce tree ->
-//     cost only for the <= 25*levels anchors that are both in-box and in-centre (every other cost
-//     carries +1e5, :104-108, so the k smallest live there unless the GT is tiny) -> k smallest
-//     (cost, anchor) -> per-anchor match count / lowest-GT atomics.
-//     The image's last GT CTA to finish (atomic counter) then finalises the image:
-//     anchors matched once take that GT; anchors matched more than once take the argmin of the cost
-//     over ALL GTs (:352-356, quirk Q4); fg_mask / matched GT / matched IoU are written densely per
-//     anchor and num_fg is counted (:357-369).
+//  K2 simota_match_kernel     one CTA (16 warps) per 8 GTs of an image
+//     1. IoU of its GTs against every candidate, candidates staged through shared memory in chunks,
+//        two warps per GT with warp-resident top-10 lists (values only, :336-340; the division runs
+//        only when a pair can enter the list) -> dynamic k with ATen's reduce tree;
+//     2. cost (:84-108) only for the <= 25 * levels anchors that are both in-box and in-centre (every
+//        other cost carries +1e5, so the k smallest live there unless the GT is tiny): one warp per
+//        (GT, anchor) pair, 80-class BCE in ATen's CUDA reduce order (lane t adds classes t, t+32,
+//        t+64, then a halving tree);
+//     3. k smallest (cost, anchor) per GT -> per-anchor match count / tentative match by atomics;
+//        anchors claimed twice are resolved right away by the argmin of the cost over ALL GTs
+//        (:352-356, quirk Q4);
+//     4. the image's last CTA to finish patches the resolved matches over the tentative ones and
+//        publishes num_fg (:357-369).
 #include <cfloat>
 
 #include "common.cuh"
@@ -30,10 +29,13 @@
 namespace plyolo {
 
 constexpr int kPrepThreads = 512;
-constexpr int kMatchWarps = 4;   // warps per GT
-constexpr int kTableCtas = 48;   // per image
-constexpr int kTableWarps = 8;
+constexpr int kPrepSplit = 4;     // CTAs per image in the prep kernel
+constexpr int kGtPerCta = 8;      // GTs per CTA in the match kernel
+constexpr int kMatchWarps = 16;   // two per GT during the IoU sweep
+constexpr int kMatchThreads = kMatchWarps * 32;
+constexpr int kChunk = 2048;      // candidates staged per pass
 constexpr int kMaxBoth = 36 * PLYOLO_MAX_LEVELS;  // 5x5 centre cells per level (6x6 if an edge rounds outward)
+constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
 
 struct SimParams {
     const float *preds;
@@ -47,14 +49,11 @@ struct SimParams {
     int32_t *num_fg;
     int32_t *num_gt;
     // workspace
-    int *meta;            // [B,8]  G, Nc, |U|, #matched anchors, #finished GT CTAs, #conflict anchors
+    int *meta;            // [B,8]  G, Nc, -, #matched anchors, #finished match CTAs, #conflict anchors
     int *conf_list;       // [B,A]  anchors claimed by more than one GT (unordered)
-    int *cand_anchor;     // [B,A]  (reused as the conflict list by the finalize kernel)
+    int *cand_anchor;     // [B,A]  candidate n -> anchor
     float4 *cand_box;     // [B,A]  corners (cx-w/2, cy-h/2, cx+w/2, cy+h/2) of candidate n
     float *cand_area;     // [B,A]  w*h of candidate n
-    int *u_anchor;        // [B,A]  anchors of U = union_g (in-box AND in-centre), ascending
-    int *u_index;         // [B,A]  position in u_anchor or -1
-    float *table;         // [B,A,C] class cost per (anchor of U, GT class)
     unsigned *sel_count;  // [B,A]  number of GTs that claimed the anchor
     int *res_g;           // [B,A]  conflict resolution: argmin GT ...
     float *res_iou;       // [B,A]  ... and its IoU
@@ -100,14 +99,27 @@ struct LaneTerms {
     float p[3];    // p = sqrt(sigmoid(cls) * sigmoid(obj))
 };
 
+// one prediction row as the lanes of a warp hold it: class logits lane + 32 j, objectness, box
+struct RawRow {
+    float x[3];
+    float obj;
+    float4 box;
+};
+__device__ __forceinline__ void load_row(const float *row, const int C, const int lane, RawRow &r) {
+    r.obj = __ldg(row + 4);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.x[j] = (lane + 32 * j < C) ? __ldg(row + 5 + lane + 32 * j) : 0.f;
+    r.box = make_float4(__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3));
+}
+
 // BCE leaves of one prediction row, lanes over classes (yolox_loss.py:94-101).
-__device__ __forceinline__ void lane_terms(const float *row, const int C, const int lane, LaneTerms &t) {
-    const float so = sigmoid_ref(__ldg(row + 4));
+__device__ __forceinline__ void lane_terms(const RawRow &r, const int C, const int lane, LaneTerms &t) {
+    const float so = sigmoid_ref(r.obj);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const int c = lane + 32 * j;
         if (c < C) {
-            const float p = sqrtf(sigmoid_ref(__ldg(row + 5 + c)) * so);
+            const float p = sqrtf(sigmoid_ref(r.x[j]) * so);
             t.p[j] = p;
             t.neg[j] = -fmaxf(log1pf(-p), -100.f);  // ATen BCE, target 0: (0-1)*max(log1p(-p),-100)
         } else {
@@ -128,9 +140,13 @@ __device__ __forceinline__ float lane_combine(const float e0, const float e1, co
 // C >= 32 path (registers only); smaller C goes through `terms` in shared memory.
 __device__ __forceinline__ float cls_cost(const LaneTerms &t, const int C, const int gc, const int lane,
                                           const bool wide, float *terms /* per-warp [96] */) {
-    float e[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) e[j] = (lane + 32 * j == gc) ? pos_term(t.p[j]) : t.neg[j];
+    float e[3] = {t.neg[0], t.neg[1], t.neg[2]};
+    if (lane == (gc & 31) && gc >= 0 && gc < 96) {  // only the lane that owns the GT class evaluates the log
+        const int j = gc >> 5;
+        const float pp = j == 0 ? t.p[0] : (j == 1 ? t.p[1] : t.p[2]);
+        const float pt = pos_term(pp);
+        if (j == 0) e[0] = pt; else if (j == 1) e[1] = pt; else e[2] = pt;
+    }
     float v;
     int lanes;
     if (C >= 32) {
@@ -181,61 +197,21 @@ __device__ __forceinline__ void set_bits(unsigned *bitmap, const int p0, const i
     }
 }
 
-// Block-wide, order-preserving compaction of the set bits of `bitmap` into `list` (+ optional inverse
-// map).  Returns the number of set bits.  All threads of the CTA must call it.
-__device__ __forceinline__ int compact_bitmap(const unsigned *bitmap, const int nwords, const int A, int *list,
-                                              int *inverse, int *s_warp) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wpt = (nwords + kPrepThreads - 1) / kPrepThreads;
-    const int w0 = min(tid * wpt, nwords), w1 = min(w0 + wpt, nwords);
-    int local = 0;
-    for (int i = w0; i < w1; ++i) {
-        unsigned m = bitmap[i];
-        if (i == nwords - 1 && (A & 31)) m &= (1u << (A & 31)) - 1u;
-        local += __popc(m);
-    }
-    int inc = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    __syncthreads();  // s_warp may still be read by a previous call
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    int base = inc - local, total = 0;
-    for (int w = 0; w < kPrepThreads / 32; ++w) {
-        if (w < warp) base += s_warp[w];
-        total += s_warp[w];
-    }
-    for (int i = w0; i < w1; ++i) {
-        unsigned m = bitmap[i];
-        if (i == nwords - 1 && (A & 31)) m &= (1u << (A & 31)) - 1u;
-        while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            const int a = (i << 5) + bit;
-            list[base] = a;
-            if (inverse) inverse[a] = base;
-            ++base;
-        }
-    }
-    return total;
-}
-
 __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimParams p) {
-    extern __shared__ unsigned bitmap[];  // [2][ceil(A/32)]: fg, U
+    extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1]
     __shared__ int s_G, s_warp[kPrepThreads / 32];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (p.A + 31) >> 5;
-    unsigned *bm_fg = bitmap, *bm_u = bitmap + nwords;
+    unsigned *bm_fg = prep_smem;
+    int *word_base = reinterpret_cast<int *>(prep_smem + nwords);
     const float *L = p.labels + (size_t)b * p.Lmax * 5;
     if (tid == 0) s_G = 0;
-    for (int i = tid; i < 2 * nwords; i += kPrepThreads) bitmap[i] = 0u;
-    for (int a = tid; a < p.A; a += kPrepThreads) {
+    for (int i = tid; i < nwords; i += kPrepThreads) bm_fg[i] = 0u;
+    // background defaults for this CTA's quarter of the anchors (:57-62); the matching overwrites the matched ones
+    const int a_per = (p.A + kPrepSplit - 1) / kPrepSplit;
+    const int a_lo = q * a_per, a_hi = min(p.A, a_lo + a_per);
+    for (int a = a_lo + tid; a < a_hi; a += kPrepThreads) {
         p.sel_count[(size_t)b * p.A + a] = 0u;
-        p.u_index[(size_t)b * p.A + a] = -1;
-        // background defaults (:57-62); the last GT CTA of the image overwrites the matched anchors
         p.fg_mask[(size_t)b * p.A + a] = 0;
         p.matched_gt[(size_t)b * p.A + a] = -1;
         p.matched_iou[(size_t)b * p.A + a] = 0.f;
@@ -261,48 +237,83 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
         const float r = 2.5f * s;                                     // :284-298, center_radius = 2.5
         cell_range(gx - r, gx + r, s, W, cx0, cx1);
         cell_range(gy - r, gy + r, s, H, cy0, cy1);
-        short *r8 = p.rect + (((size_t)b * p.Lmax + g) * p.n_levels + l) * 8;
-        r8[0] = (short)bx0; r8[1] = (short)bx1; r8[2] = (short)by0; r8[3] = (short)by1;
-        r8[4] = (short)cx0; r8[5] = (short)cx1; r8[6] = (short)cy0; r8[7] = (short)cy1;
+        if (q == 0) {
+            short *r8 = p.rect + (((size_t)b * p.Lmax + g) * p.n_levels + l) * 8;
+            r8[0] = (short)bx0; r8[1] = (short)bx1; r8[2] = (short)by0; r8[3] = (short)by1;
+            r8[4] = (short)cx0; r8[5] = (short)cx1; r8[6] = (short)cy0; r8[7] = (short)cy1;
+        }
         const int o = p.off[l];
         if (bx0 <= bx1)
             for (int y = by0; y <= by1; ++y) set_bits(bm_fg, o + y * W + bx0, o + y * W + bx1);
         if (cx0 <= cx1)
             for (int y = cy0; y <= cy1; ++y) set_bits(bm_fg, o + y * W + cx0, o + y * W + cx1);
-        const int ux0 = max(bx0, cx0), ux1 = min(bx1, cx1), uy0 = max(by0, cy0), uy1 = min(by1, cy1);
-        if (ux0 <= ux1)
-            for (int y = uy0; y <= uy1; ++y) set_bits(bm_u, o + y * W + ux0, o + y * W + ux1);
     }
     __syncthreads();
 
-    // candidates in anchor order: candidate n <-> n-th set bit of fg (:79-82); same for U
+    // exclusive prefix of the word popcounts: candidate n <-> n-th set bit of fg (:79-82)
+    int run = 0;  // same value in every thread
+    for (int w0 = 0; w0 < nwords; w0 += kPrepThreads) {
+        const int w = w0 + tid;
+        unsigned m = w < nwords ? bm_fg[w] : 0u;
+        if (w == nwords - 1 && (p.A & 31)) m &= (1u << (p.A & 31)) - 1u;
+        const int c = __popc(m);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int base = run, tot = 0;
+#pragma unroll
+        for (int k = 0; k < kPrepThreads / 32; ++k) {
+            if (k < warp) base += s_warp[k];
+            tot += s_warp[k];
+        }
+        if (w < nwords) word_base[w] = base + inc - c;
+        run += tot;
+        __syncthreads();
+    }
+    const int Nc = run;
+    // this CTA's quarter of the words: candidate list, then the gather of the candidates' boxes
+    const int w_per = (nwords + kPrepSplit - 1) / kPrepSplit;
+    const int w_lo = min(q * w_per, nwords), w_hi = min(w_lo + w_per, nwords);
     int *ca = p.cand_anchor + (size_t)b * p.A;
-    const int Nc = compact_bitmap(bm_fg, nwords, p.A, ca, nullptr, s_warp);
-    const int U = compact_bitmap(bm_u, nwords, p.A, p.u_anchor + (size_t)b * p.A, p.u_index + (size_t)b * p.A, s_warp);
-    __syncthreads();  // the candidate list (global) is complete for this CTA
+    for (int w = w_lo + tid; w < w_hi; w += kPrepThreads) {
+        unsigned m = bm_fg[w];
+        if (w == nwords - 1 && (p.A & 31)) m &= (1u << (p.A & 31)) - 1u;
+        int n = word_base[w];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            ca[n++] = (w << 5) + bit;
+        }
+    }
+    __syncthreads();  // this CTA's part of the candidate list (global) is complete
+    const int n_lo = w_lo < nwords ? word_base[w_lo] : Nc, n_hi = w_hi < nwords ? word_base[w_hi] : Nc;
     float4 *cb = p.cand_box + (size_t)b * p.A;
     float *car = p.cand_area + (size_t)b * p.A;
-    for (int n0 = tid; n0 < Nc; n0 += 4 * kPrepThreads) {
+    for (int n0 = n_lo + tid; n0 < n_hi; n0 += 4 * kPrepThreads) {
         float4 pb[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {  // 4 independent row gathers in flight per thread
             const int n = n0 + u * kPrepThreads;
-            if (n < Nc) pb[u] = load_box(p.preds + ((size_t)b * p.A + ca[n]) * p.ch);
+            if (n < n_hi) pb[u] = load_box(p.preds + ((size_t)b * p.A + ca[n]) * p.ch);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int n = n0 + u * kPrepThreads;
-            if (n < Nc) {
+            if (n < n_hi) {
                 // the candidate-side operands of bboxes_iou(xyxy=False) (iou_loss.py:400-410)
                 cb[n] = make_float4(pb[u].x - pb[u].z / 2, pb[u].y - pb[u].w / 2, pb[u].x + pb[u].z / 2, pb[u].y + pb[u].w / 2);
                 car[n] = pb[u].z * pb[u].w;
             }
         }
     }
-    if (tid == 0) {
+    if (q == 0 && tid == 0) {
         p.meta[b * 8 + 0] = G;
         p.meta[b * 8 + 1] = Nc;
-        p.meta[b * 8 + 2] = U;
         p.meta[b * 8 + 3] = 0;
         p.meta[b * 8 + 4] = 0;
         p.meta[b * 8 + 5] = 0;
@@ -311,53 +322,25 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
     }
 }
 
-// ---- K2 ------------------------------------------------------------------------------------
-// Class-cost table: T[u][c] = sum over classes of BCE(p, onehot(c)) for anchor u_anchor[u], in ATen's
-// CUDA reduce order (only used when C >= 32; smaller class counts take the pair_cost path).
-__global__ void __launch_bounds__(kTableWarps * 32) simota_cost_table_kernel(const SimParams p) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1], U = p.meta[b * 8 + 2];
-    const bool wide = (long long)G * Nc < 16 && p.C >= 64;
-    const int *ua = p.u_anchor + (size_t)b * p.A;
-    for (int u = blockIdx.x * kTableWarps + warp; u < U; u += kTableCtas * kTableWarps) {
-        const float *row = p.preds + ((size_t)b * p.A + ua[u]) * p.ch;
-        LaneTerms t;
-        lane_terms(row, p.C, lane, t);
-        float s = lane_combine(t.neg[0], t.neg[1], t.neg[2], wide);
-        float sib[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            sib[i] = __shfl_xor_sync(0xffffffffu, s, 16 >> i);
-            s = s + sib[i];
-        }
-        float *T = p.table + ((size_t)b * p.A + u) * p.C;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = lane + 32 * j;
-            if (c < p.C) {
-                const float e0 = j == 0 ? pos_term(t.p[0]) : t.neg[0];
-                const float e1 = j == 1 ? pos_term(t.p[1]) : t.neg[1];
-                const float e2 = j == 2 ? pos_term(t.p[2]) : t.neg[2];
-                float r = lane_combine(e0, e1, e2, wide);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) r = r + sib[i];
-                T[c] = r;
-            }
-        }
-    }
+// cost of (GT, anchor row) exactly as yolox_loss.py:84-108; warp-cooperative, valid in lane 0; *iou_out = IoU
+__device__ __forceinline__ float pair_cost_row(const SimParams &p, const RawRow &r, const float gx, const float gy,
+                                               const float gw, const float gh, const int gc, const bool both,
+                                               const bool wide, const int lane, float *terms, float *iou_out) {
+    LaneTerms t;
+    lane_terms(r, p.C, lane, t);
+    const float lcls = cls_cost(t, p.C, gc, lane, wide, terms);
+    const float iou = pair_iou(gx, gy, gw, gh, r.box);
+    const float liou = -logf(iou + 1e-8f);                          // :86
+    *iou_out = iou;
+    return (lcls + 3.0f * liou) + (both ? 0.0f : 100000.0f);        // :104-108
 }
-
-// cost of (GT g, anchor a) exactly as yolox_loss.py:84-108; warp-cooperative, valid in lane 0
 __device__ __forceinline__ float pair_cost(const SimParams &p, const int b, const int a, const float gx,
                                            const float gy, const float gw, const float gh, const int gc,
-                                           const bool both, const bool wide, const int lane, float *terms) {
-    const float *row = p.preds + ((size_t)b * p.A + a) * p.ch;
-    LaneTerms t;
-    lane_terms(row, p.C, lane, t);
-    const float lcls = cls_cost(t, p.C, gc, lane, wide, terms);
-    const float iou = pair_iou(gx, gy, gw, gh, load_box(row));
-    const float liou = -logf(iou + 1e-8f);                          // :86
-    return (lcls + 3.0f * liou) + (both ? 0.0f : 100000.0f);        // :104-108
+                                           const bool both, const bool wide, const int lane, float *terms,
+                                           float *iou_out) {
+    RawRow r;
+    load_row(p.preds + ((size_t)b * p.A + a) * p.ch, p.C, lane, r);
+    return pair_cost_row(p, r, gx, gy, gw, gh, gc, both, wide, lane, terms, iou_out);
 }
 
 // inserts x into a descending list held one value per lane (lane i = i-th largest)
@@ -381,210 +364,10 @@ __device__ __forceinline__ bool claim(const SimParams &p, const int b, const int
     return old == 1u;
 }
 
-__device__ void resolve_conflict(const SimParams &p, const int b, const int a, const int G, const bool wide, float *T);
-
-// ---- K3 ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMatchWarps * 32) simota_match_kernel(const SimParams p) {
-    __shared__ int s_anchor[kMaxBoth];
-    __shared__ float s_cost[kMaxBoth];
-    __shared__ float s_terms[96];
-    __shared__ float s_iou[kMaxBoth];
-    __shared__ float s_top[kMatchWarps][10];
-    __shared__ float s_T[kMatchWarps][96];
-    __shared__ int s_conf[64];
-    __shared__ int s_k, s_nb, s_last, s_nc;
-    const int b = blockIdx.y, g = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
-    if (g >= G || Nc == 0) return;
-    const float *L = p.labels + ((size_t)b * p.Lmax + g) * 5;
-    const int gc = (int)L[0];  // .to(int64) truncates (:89)
-    const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
-    const int *ca = p.cand_anchor + (size_t)b * p.A;
-    const float4 *cb = p.cand_box + (size_t)b * p.A;
-    const float *car = p.cand_area + (size_t)b * p.A;
-    // ATen picks a 64-wide block for sum(-1) when the [G,Nc] output has fewer than 16 elements (and C >= 64)
-    const bool wide = (long long)G * Nc < 16 && p.C >= 64;
-
-    // ---- top-10 IoU values over all candidates (iou_loss.py:400-414 with xyxy=False; GT-side operands
-    // hoisted).  Lists start at +0: a pair that does not overlap has IoU (+/-)0 and can never displace
-    // anything; the division runs only when the quotient could exceed the current 10th value.
-    const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
-    const float area_a = gw * gh;
-    float top = 0.f, thresh = 0.f;
-    const int per = (((Nc + kMatchWarps - 1) / kMatchWarps) + 31) & ~31;
-    const int n_lo = warp * per, n_hi = min(Nc, n_lo + per);
-    for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
-        const int n = n0 + lane;
-        float v = 0.f;
-        if (n < n_hi) {
-            const float4 c = cb[n];
-            const float tlx = fmaxf(g_x1, c.x), tly = fmaxf(g_y1, c.y);
-            const float brx = fminf(g_x2, c.z), bry = fminf(g_y2, c.w);
-            if (tlx < brx && tly < bry) {  // en == 1
-                const float area_i = (brx - tlx) * (bry - tly);
-                const float den = (area_a + car[n]) - area_i;
-                if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
-            }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, v > thresh);
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            top_insert(top, __shfl_sync(0xffffffffu, v, j), lane);
-        }
-        thresh = __shfl_sync(0xffffffffu, top, 9);
-    }
-    if (lane < 10) s_top[warp][lane] = top;
-    __syncthreads();
-    if (warp == 0) {
-        const int src = lane + 10;  // the other warps' 30 values
-        const float mine = (src < 10 * kMatchWarps) ? s_top[src / 10][src % 10] : 0.f;
-        for (int j = 0; j < 10 * (kMatchWarps - 1); ++j) {
-            const float x = __shfl_sync(0xffffffffu, mine, j);
-            if (x > thresh) {
-                top_insert(top, x, lane);
-                thresh = __shfl_sync(0xffffffffu, top, 9);
-            }
-        }
-        // dynamic k = clamp(int(sum of the top min(10, Nc)), 1) with ATen's reduce tree (:336-340)
-        const int kc = min(10, Nc);
-        int bw = 1;
-        while (bw * 2 <= kc) bw <<= 1;
-        const float hi = __shfl_down_sync(0xffffffffu, top, bw);
-        float v = 0.f;
-        if (lane < bw) v = top + ((lane + bw < kc) ? hi : 0.f);
-        for (int h = bw >> 1; h >= 1; h >>= 1) {
-            const float o = __shfl_down_sync(0xffffffffu, v, h);
-            if (lane < h) v = v + o;
-        }
-        const int k = max((int)__shfl_sync(0xffffffffu, v, 0), 1);
-        // ---- anchors both in-box and in-centre, in ascending anchor order
-        const short *rect = p.rect + ((size_t)b * p.Lmax + g) * p.n_levels * 8;
-        int nb = 0;
-        if (k < Nc - 1) {
-            for (int l = 0; l < p.n_levels; ++l) {
-                const short *r8 = rect + l * 8;
-                const int x0 = max(r8[0], r8[4]), x1 = min(r8[1], r8[5]);
-                const int y0 = max(r8[2], r8[6]), y1 = min(r8[3], r8[7]);
-                if (x0 > x1 || y0 > y1) continue;
-                const int wx = x1 - x0 + 1, cells = wx * (y1 - y0 + 1);
-                for (int i = lane; i < cells; i += 32)
-                    if (nb + i < kMaxBoth) s_anchor[nb + i] = p.off[l] + (y0 + i / wx) * p.w[l] + x0 + i % wx;
-                nb = min(nb + cells, kMaxBoth);
-            }
-        }
-        if (lane == 0) { s_k = k; s_nb = nb; s_nc = 0; }
-    }
-    __syncthreads();
-    const int k = s_k, nb = s_nb;
-    auto push_conflict = [&](const int a) {
-        const int i = atomicAdd(&s_nc, 1);
-        if (i < 64) s_conf[i] = a;
-    };
-
-    if (!(k < Nc - 1)) {  // quirk Q3 (:343): the GT takes EVERY candidate
-        for (int n = tid; n < Nc; n += kMatchWarps * 32) {  // Nc <= 11 here (k <= 10)
-            const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + ca[n]) * p.ch));
-            if (claim(p, b, ca[n], g, iou)) push_conflict(ca[n]);
-        }
-    } else {
-        // ---- cost of the in-both anchors (:84-108): class cost from the table, IoU term on the fly
-        if (p.C >= 32) {
-            const int *uidx = p.u_index + (size_t)b * p.A;
-            const int gcc = min(max(gc, 0), p.C - 1);
-            for (int i = tid; i < nb; i += kMatchWarps * 32) {
-                const int a = s_anchor[i];
-                const float lcls = p.table[((size_t)b * p.A + uidx[a]) * p.C + gcc];
-                const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + a) * p.ch));
-                const float liou = -logf(iou + 1e-8f);     // :86
-                s_cost[i] = (lcls + 3.0f * liou) + 0.0f;   // :104-108 (in_boxes_and_center -> + 1e5 * 0)
-                s_iou[i] = iou;
-            }
-        } else if (warp == 0) {
-            for (int i = 0; i < nb; ++i) {
-                const float c = pair_cost(p, b, s_anchor[i], gx, gy, gw, gh, gc, true, wide, lane, s_terms);
-                if (lane == 0) {
-                    s_cost[i] = c;
-                    s_iou[i] = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + s_anchor[i]) * p.ch));
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // ---- k smallest (cost, anchor); ties -> lowest anchor index (stable sort, :342)
-            const int take = min(k, nb);
-            for (int r = 0; r < take; ++r) {
-                unsigned long long best = ~0ull;
-                for (int i = lane; i < nb; i += 32) {
-                    const float c = s_cost[i];
-                    if (c >= 0.f || c < 0.f) {  // not yet taken (taken entries are NaN)
-                        const unsigned long long key = ((unsigned long long)float_ordered(c) << 32) | (unsigned)i;
-                        best = key < best ? key : best;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-                    best = other < best ? other : best;
-                }
-                const int i = (int)(best & 0xffffffffu);
-                if (lane == 0) {
-                    if (claim(p, b, s_anchor[i], g, s_iou[i])) push_conflict(s_anchor[i]);
-                    s_cost[i] = __int_as_float(0x7fc00000);
-                }
-                __syncwarp();
-            }
-            if (k > nb) {
-                // ---- tiny GT: fewer in-both anchors than k.  The remaining picks come from the candidates
-                // whose cost carries +1e5 (quantised to 1/128, T8): smallest (cost, anchor) over all others.
-                const short *rect = p.rect + ((size_t)b * p.Lmax + g) * p.n_levels * 8;
-                const int need = k - nb;  // <= 10
-                unsigned long long mine = ~0ull;  // lanes 0..need-1 hold the `need` smallest keys, ascending
-                for (int n = 0; n < Nc; ++n) {
-                    const int a = ca[n];
-                    int l, x, y;
-                    anchor_cell(p, a, l, x, y);
-                    if (in_both(rect + l * 8, x, y)) continue;
-                    float c = pair_cost(p, b, a, gx, gy, gw, gh, gc, false, wide, lane, s_terms);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    const unsigned long long key = ((unsigned long long)float_ordered(c) << 32) | (unsigned)a;
-                    const unsigned long long upk = __shfl_up_sync(0xffffffffu, mine, 1);
-                    if (key < mine) mine = (lane == 0 || upk <= key) ? key : upk;
-                }
-                if (lane < need && mine != ~0ull) {
-                    const int a = (int)(mine & 0xffffffffu);
-                    const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + a) * p.ch));
-                    if (claim(p, b, a, g, iou)) push_conflict(a);
-                }
-            }
-        }
-    }
-
-    // ---- resolve the conflicts this CTA created (one warp each)
-    __syncthreads();
-    const int nc = min(s_nc, 64);
-    for (int i = warp; i < nc; i += kMatchWarps) resolve_conflict(p, b, s_conf[i], G, wide, s_T[warp]);
-
-    // ---- the last GT CTA of the image to finish patches the resolved matches over the tentative ones
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&p.meta[b * 8 + 4], 1) == G - 1) ? 1 : 0;
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        const int nconf = __ldcg(p.meta + b * 8 + 5);
-        for (int i = tid; i < nconf; i += kMatchWarps * 32) {
-            const int a = __ldcg(p.conf_list + (size_t)b * p.A + i);
-            p.matched_gt[(size_t)b * p.A + a] = __ldcg(p.res_g + (size_t)b * p.A + a);
-            p.matched_iou[(size_t)b * p.A + a] = __ldcg(p.res_iou + (size_t)b * p.A + a);
-        }
-        if (tid == 0) p.num_fg[b] = __ldcg(p.meta + b * 8 + 3);  // :358
-    }
-}
-
-// ---- conflict resolution (warp-cooperative) -----------------------------------------------------
-// anchor a was claimed by several GTs: argmin of the cost column over ALL GT rows, first minimum (:352-356)
+// anchor a was claimed by several GTs: argmin of the cost column over ALL GT rows, first minimum (:352-356).
+// Warp-cooperative.  The class costs of the anchor for every possible GT class come from one reduction in
+// ATen's order: a butterfly over the all-negative leaves leaves each lane the sibling sums of its path, and
+// swapping in the positive leaf re-adds them (C >= 32); smaller class counts evaluate every pair.
 __device__ void resolve_conflict(const SimParams &p, const int b, const int a, const int G, const bool wide, float *T) {
     const int lane = threadIdx.x & 31;
     const float *L = p.labels + (size_t)b * p.Lmax * 5;
@@ -594,34 +377,28 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
     anchor_cell(p, a, l, x, y);
     const bool fast = p.C >= 32;
     if (fast) {
-        const int u = p.u_index[(size_t)b * p.A + a];
-        if (u >= 0) {
-            const float *src = p.table + ((size_t)b * p.A + u) * p.C;
-            for (int c = lane; c < 96; c += 32) T[c] = c < p.C ? src[c] : 0.f;
-        } else {
-            // not in any in-both set (claimed through the +1e5 region): class costs from one reduction,
-            // butterfly over the all-negative leaves + positive-leaf swap (same tree as the table kernel)
-            LaneTerms t;
-            lane_terms(row, p.C, lane, t);
-            float s = lane_combine(t.neg[0], t.neg[1], t.neg[2], wide);
-            float sib[5];
+        RawRow rr;
+        load_row(row, p.C, lane, rr);
+        LaneTerms t;
+        lane_terms(rr, p.C, lane, t);
+        float s = lane_combine(t.neg[0], t.neg[1], t.neg[2], wide);
+        float sib[5];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                sib[i] = __shfl_xor_sync(0xffffffffu, s, 16 >> i);
-                s = s + sib[i];
-            }
+        for (int i = 0; i < 5; ++i) {
+            sib[i] = __shfl_xor_sync(0xffffffffu, s, 16 >> i);
+            s = s + sib[i];
+        }
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int c = lane + 32 * j;
-                if (c < p.C) {
-                    const float e0 = j == 0 ? pos_term(t.p[0]) : t.neg[0];
-                    const float e1 = j == 1 ? pos_term(t.p[1]) : t.neg[1];
-                    const float e2 = j == 2 ? pos_term(t.p[2]) : t.neg[2];
-                    float r = lane_combine(e0, e1, e2, wide);
+        for (int j = 0; j < 3; ++j) {
+            const int c = lane + 32 * j;
+            if (c < p.C) {
+                const float e0 = j == 0 ? pos_term(t.p[0]) : t.neg[0];
+                const float e1 = j == 1 ? pos_term(t.p[1]) : t.neg[1];
+                const float e2 = j == 2 ? pos_term(t.p[2]) : t.neg[2];
+                float r = lane_combine(e0, e1, e2, wide);
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) r = r + sib[i];
-                    T[c] = r;
-                }
+                for (int i = 0; i < 5; ++i) r = r + sib[i];
+                T[c] = r;
             }
         }
         __syncwarp();
@@ -641,7 +418,8 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
         for (int g = 0; g < G; ++g) {
             const float *gr = L + 5 * g;
             const short *r8 = p.rect + (((size_t)b * p.Lmax + g) * p.n_levels + l) * 8;
-            const float cost = pair_cost(p, b, a, gr[1], gr[2], gr[3], gr[4], (int)gr[0], in_both(r8, x, y), wide, lane, T);
+            float iou;
+            const float cost = pair_cost(p, b, a, gr[1], gr[2], gr[3], gr[4], (int)gr[0], in_both(r8, x, y), wide, lane, T, &iou);
             if (lane == 0) {
                 const unsigned long long key = ((unsigned long long)float_ordered(cost) << 32) | (unsigned)g;
                 best = key < best ? key : best;
@@ -663,6 +441,265 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
     __syncwarp();
 }
 
+// ---- K2 ------------------------------------------------------------------------------------
+struct MatchShared {
+    float4 cbox[kChunk];
+    float carea[kChunk];
+    int anchor[kGtPerCta][kMaxBoth];
+    float cost[kGtPerCta][kMaxBoth];
+    float iou[kGtPerCta][kMaxBoth];
+    float top[kMatchWarps][10];
+    float terms[kMatchWarps][96];
+    int conf[kMaxConf];
+    int k[kGtPerCta], nb[kGtPerCta];
+    int nconf, last;
+};
+
+__global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimParams p) {
+    extern __shared__ __align__(16) unsigned char match_smem[];
+    MatchShared &sh = *reinterpret_cast<MatchShared *>(match_smem);
+    const int b = blockIdx.y, g0 = blockIdx.x * kGtPerCta;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
+    if (g0 >= G || Nc == 0) return;
+    const int n_active = (G + kGtPerCta - 1) / kGtPerCta;  // CTAs of this image that reach the end
+    const int gi = warp & (kGtPerCta - 1), half = warp / kGtPerCta;  // IoU sweep: GT and candidate half of this warp
+    const int g = g0 + gi;
+    const bool live = g < G;
+    const float *L = p.labels + ((size_t)b * p.Lmax + (live ? g : g0)) * 5;
+    const int gc = (int)L[0];  // .to(int64) truncates (:89)
+    const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
+    const int *ca = p.cand_anchor + (size_t)b * p.A;
+    const float4 *cb = p.cand_box + (size_t)b * p.A;
+    const float *car = p.cand_area + (size_t)b * p.A;
+    // ATen picks a 64-wide block for sum(-1) when the [G,Nc] output has fewer than 16 elements (and C >= 64)
+    const bool wide = (long long)G * Nc < 16 && p.C >= 64;
+    if (tid == 0) sh.nconf = 0;
+
+    // ---- 0. anchors both in-box and in-centre of every GT of the CTA (ascending anchor order; closed form from
+    // the rectangles) and an L2 prefetch of their prediction rows: the IoU sweep below hides the DRAM latency
+    if (half == 0) {
+        int nb = 0;
+        if (live) {
+            const short *rect = p.rect + ((size_t)b * p.Lmax + g) * p.n_levels * 8;
+            for (int l = 0; l < p.n_levels; ++l) {
+                const short *r8 = rect + l * 8;
+                const int x0 = max(r8[0], r8[4]), x1 = min(r8[1], r8[5]);
+                const int y0 = max(r8[2], r8[6]), y1 = min(r8[3], r8[7]);
+                if (x0 > x1 || y0 > y1) continue;
+                const int wx = x1 - x0 + 1, cells = wx * (y1 - y0 + 1);
+                for (int i = lane; i < cells; i += 32) {
+                    if (nb + i < kMaxBoth) {
+                        const int a = p.off[l] + (y0 + i / wx) * p.w[l] + x0 + i % wx;
+                        sh.anchor[gi][nb + i] = a;
+                        const char *row = reinterpret_cast<const char *>(p.preds + ((size_t)b * p.A + a) * p.ch);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 256));
+                        if (p.ch * 4 > 384 - 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + p.ch * 4 - 4));
+                    }
+                }
+                nb = min(nb + cells, kMaxBoth);
+            }
+        }
+        if (lane == 0) sh.nb[gi] = nb;
+    }
+
+    // ---- 1. top-10 IoU values over all candidates (iou_loss.py:400-414 with xyxy=False; GT-side operands
+    // hoisted).  Lists start at +0: a pair that does not overlap has IoU (+/-)0 and can never displace
+    // anything; the division runs only when the quotient could exceed the current 10th value.
+    const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
+    const float area_a = gw * gh;
+    float top = 0.f, thresh = 0.f;
+    for (int c0 = 0; c0 < Nc; c0 += kChunk) {
+        const int cn = min(kChunk, Nc - c0);
+        __syncthreads();  // the previous chunk is no longer read
+        for (int i = tid; i < cn; i += kMatchThreads) {
+            sh.cbox[i] = cb[c0 + i];
+            sh.carea[i] = car[c0 + i];
+        }
+        __syncthreads();
+        if (live) {
+            const int per = (((cn + 1) >> 1) + 31) & ~31;
+            const int n_lo = half * per, n_hi = min(cn, n_lo + per);
+            for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
+                const int n = n0 + lane;
+                float v = 0.f;
+                if (n < n_hi) {
+                    const float4 c = sh.cbox[n];
+                    const float tlx = fmaxf(g_x1, c.x), tly = fmaxf(g_y1, c.y);
+                    const float brx = fminf(g_x2, c.z), bry = fminf(g_y2, c.w);
+                    if (tlx < brx && tly < bry) {  // en == 1
+                        const float area_i = (brx - tlx) * (bry - tly);
+                        const float den = (area_a + sh.carea[n]) - area_i;
+                        if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, v > thresh);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    top_insert(top, __shfl_sync(0xffffffffu, v, j), lane);
+                }
+                thresh = __shfl_sync(0xffffffffu, top, 9);
+            }
+        }
+    }
+    if (lane < 10) sh.top[warp][lane] = top;
+    __syncthreads();
+    if (half == 0 && live) {
+        const float mine = lane < 10 ? sh.top[warp + kGtPerCta][lane] : 0.f;  // the partner warp's 10 values
+        for (int j = 0; j < 10; ++j) {
+            const float x = __shfl_sync(0xffffffffu, mine, j);
+            if (x > thresh) {
+                top_insert(top, x, lane);
+                thresh = __shfl_sync(0xffffffffu, top, 9);
+            }
+        }
+        // dynamic k = clamp(int(sum of the top min(10, Nc)), 1) with ATen's reduce tree (:336-340)
+        const int kc = min(10, Nc);
+        int bw = 1;
+        while (bw * 2 <= kc) bw <<= 1;
+        const float hi = __shfl_down_sync(0xffffffffu, top, bw);
+        float v = 0.f;
+        if (lane < bw) v = top + ((lane + bw < kc) ? hi : 0.f);
+        for (int h = bw >> 1; h >= 1; h >>= 1) {
+            const float o = __shfl_down_sync(0xffffffffu, v, h);
+            if (lane < h) v = v + o;
+        }
+        const int k = max((int)__shfl_sync(0xffffffffu, v, 0), 1);
+        if (lane == 0) {
+            sh.k[gi] = k;
+            if (!(k < Nc - 1)) sh.nb[gi] = 0;  // quirk Q3: every candidate is taken, no cost needed
+        }
+    } else if (half == 0 && lane == 0) {
+        sh.k[gi] = 0;
+    }
+    __syncthreads();
+
+    // ---- 2. cost of the in-both anchors (:84-108), one warp per (GT, anchor) pair.  The pairs of the CTA's GTs
+    // form one flat list; every warp walks it with stride 16 and loads the NEXT pair's prediction row (DRAM:
+    // 340 of the row's bytes, three coalesced requests) before it evaluates the current one.
+    {
+        int pbase[kGtPerCta + 1];
+        pbase[0] = 0;
+#pragma unroll
+        for (int q = 0; q < kGtPerCta; ++q) pbase[q + 1] = pbase[q] + sh.nb[q];
+        const int npairs = pbase[kGtPerCta];
+        auto locate = [&](const int t, int &q, int &i) {
+            q = 0;
+            int base = 0;
+#pragma unroll
+            for (int u = 1; u < kGtPerCta; ++u)
+                if (t >= pbase[u]) { q = u; base = pbase[u]; }
+            i = t - base;
+        };
+        RawRow cur, nxt;
+        int q = 0, i = 0;
+        if (warp < npairs) {
+            locate(warp, q, i);
+            load_row(p.preds + ((size_t)b * p.A + sh.anchor[q][i]) * p.ch, p.C, lane, cur);
+        }
+        for (int t = warp; t < npairs; t += kMatchWarps) {
+            int qn = 0, in_ = 0;
+            const bool more = t + kMatchWarps < npairs;
+            if (more) {
+                locate(t + kMatchWarps, qn, in_);
+                load_row(p.preds + ((size_t)b * p.A + sh.anchor[qn][in_]) * p.ch, p.C, lane, nxt);
+            }
+            const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
+            float iou;
+            const float c = pair_cost_row(p, cur, Lq[1], Lq[2], Lq[3], Lq[4], (int)Lq[0], true, wide, lane, sh.terms[warp], &iou);
+            if (lane == 0) { sh.cost[q][i] = c; sh.iou[q][i] = iou; }
+            if (more) { cur = nxt; q = qn; i = in_; }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. per GT (first 8 warps): k smallest (cost, anchor); ties -> lowest anchor index (stable sort, :342)
+    auto push_conflict = [&](const int a) {
+        const int i = atomicAdd(&sh.nconf, 1);
+        if (i < kMaxConf) sh.conf[i] = a;
+    };
+    if (half == 0 && live) {
+        const int k = sh.k[gi], nb = sh.nb[gi];
+        if (!(k < Nc - 1)) {  // quirk Q3 (:343): the GT takes EVERY candidate (Nc <= 11 here, k <= 10)
+            for (int n = lane; n < Nc; n += 32) {
+                const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + ca[n]) * p.ch));
+                if (claim(p, b, ca[n], g, iou)) push_conflict(ca[n]);
+            }
+        } else {
+            const int take = min(k, nb);
+            for (int r = 0; r < take; ++r) {
+                unsigned long long best = ~0ull;
+                for (int i = lane; i < nb; i += 32) {
+                    const float c = sh.cost[gi][i];
+                    if (c >= 0.f || c < 0.f) {  // not yet taken (taken entries are NaN)
+                        const unsigned long long key = ((unsigned long long)float_ordered(c) << 32) | (unsigned)i;
+                        best = key < best ? key : best;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = other < best ? other : best;
+                }
+                const int i = (int)(best & 0xffffffffu);
+                if (lane == 0) {
+                    if (claim(p, b, sh.anchor[gi][i], g, sh.iou[gi][i])) push_conflict(sh.anchor[gi][i]);
+                    sh.cost[gi][i] = __int_as_float(0x7fc00000);
+                }
+                __syncwarp();
+            }
+            if (k > nb) {
+                // ---- tiny GT: fewer in-both anchors than k.  The remaining picks come from the candidates
+                // whose cost carries +1e5 (quantised to 1/128, T8): smallest (cost, anchor) over all others.
+                const short *rect = p.rect + ((size_t)b * p.Lmax + g) * p.n_levels * 8;
+                const int need = k - nb;  // <= 10
+                unsigned long long mine = ~0ull;  // lanes 0..need-1 hold the `need` smallest keys, ascending
+                for (int n = 0; n < Nc; ++n) {
+                    const int a = ca[n];
+                    int l, x, y;
+                    anchor_cell(p, a, l, x, y);
+                    if (in_both(rect + l * 8, x, y)) continue;
+                    float iou;
+                    float c = pair_cost(p, b, a, gx, gy, gw, gh, gc, false, wide, lane, sh.terms[warp], &iou);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    const unsigned long long key = ((unsigned long long)float_ordered(c) << 32) | (unsigned)a;
+                    const unsigned long long upk = __shfl_up_sync(0xffffffffu, mine, 1);
+                    if (key < mine) mine = (lane == 0 || upk <= key) ? key : upk;
+                }
+                if (lane < need && mine != ~0ull) {
+                    const int a = (int)(mine & 0xffffffffu);
+                    const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + a) * p.ch));
+                    if (claim(p, b, a, g, iou)) push_conflict(a);
+                }
+            }
+        }
+    }
+
+    // ---- resolve the conflicts this CTA created (one warp each)
+    __syncthreads();
+    const int nc = min(sh.nconf, kMaxConf);
+    for (int i = warp; i < nc; i += kMatchWarps) resolve_conflict(p, b, sh.conf[i], G, wide, sh.terms[warp]);
+
+    // ---- 4. the last CTA of the image to finish patches the resolved matches over the tentative ones
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh.last = (atomicAdd(&p.meta[b * 8 + 4], 1) == n_active - 1) ? 1 : 0;
+    __syncthreads();
+    if (sh.last) {
+        __threadfence();
+        const int nconf = __ldcg(p.meta + b * 8 + 5);
+        for (int i = tid; i < nconf; i += kMatchThreads) {
+            const int a = __ldcg(p.conf_list + (size_t)b * p.A + i);
+            p.matched_gt[(size_t)b * p.A + a] = __ldcg(p.res_g + (size_t)b * p.A + a);
+            p.matched_iou[(size_t)b * p.A + a] = __ldcg(p.res_iou + (size_t)b * p.A + a);
+        }
+        if (tid == 0) p.num_fg[b] = __ldcg(p.meta + b * 8 + 3);  // :358
+    }
+}
+
 static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, unsigned char *base) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -672,9 +709,6 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
     const size_t o_ca = take((size_t)B * A * sizeof(int));
     const size_t o_cb = take((size_t)B * A * sizeof(float4));
     const size_t o_car = take((size_t)B * A * sizeof(float));
-    const size_t o_ua = take((size_t)B * A * sizeof(int));
-    const size_t o_ui = take((size_t)B * A * sizeof(int));
-    const size_t o_tab = take((size_t)B * A * PLYOLO_MAX_CLASSES * sizeof(float));
     const size_t o_sc = take((size_t)B * A * sizeof(unsigned));
     const size_t o_sm = take((size_t)B * A * sizeof(unsigned));
     const size_t o_rect = take((size_t)B * Lmax * n_levels * 8 * sizeof(short));
@@ -685,9 +719,6 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
         p->cand_anchor = reinterpret_cast<int *>(base + o_ca);
         p->cand_box = reinterpret_cast<float4 *>(base + o_cb);
         p->cand_area = reinterpret_cast<float *>(base + o_car);
-        p->u_anchor = reinterpret_cast<int *>(base + o_ua);
-        p->u_index = reinterpret_cast<int *>(base + o_ui);
-        p->table = reinterpret_cast<float *>(base + o_tab);
         p->sel_count = reinterpret_cast<unsigned *>(base + o_sc);
         p->res_g = reinterpret_cast<int *>(base + o_sm);
         p->rect = reinterpret_cast<short *>(base + o_rect);
@@ -741,16 +772,13 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     p.fg_mask = fg_mask; p.matched_gt = matched_gt; p.matched_iou = matched_iou; p.num_fg = num_fg; p.num_gt = num_gt;
     sim_ws_layout(B, A, Lmax, n_levels, &p, static_cast<unsigned char *>(workspace));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t bm = 2 * (size_t)((A + 31) / 32) * sizeof(unsigned);
-    PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmaps", A);
+    const size_t bm = (2 * (size_t)((A + 31) / 32) + 1) * sizeof(unsigned);
+    PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
     if (bm > 40 * 1024) cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm);
-    simota_prep_kernel<<<B, kPrepThreads, bm, st>>>(p);
+    simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
-    if (C >= 32) {
-        simota_cost_table_kernel<<<dim3(kTableCtas, B), kTableWarps * 32, 0, st>>>(p);
-        PLYOLO_CHECK_LAUNCH("simota_cost_table_kernel");
-    }
-    simota_match_kernel<<<dim3(Lmax, B), kMatchWarps * 32, 0, st>>>(p);
+    cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));
+    simota_match_kernel<<<dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), kMatchThreads, sizeof(MatchShared), st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_match_kernel");
     return PLYOLO_OK;
 }
