@@ -17,6 +17,9 @@ namespace plyolo {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_device();  // PLYOLO_OK or PLYOLO_ERR_NO_DEVICE
+// debug hook: records the calling thread's stage event `i` (0 = before the first kernel of an entry point,
+// 1 = between its two kernels, 2 = after the last) on `stream` if plyolo_debug_stage_events() armed them
+void record_stage_event(int i, cudaStream_t stream);
 
 #define PLYOLO_CHECK_LAUNCH(what)                                                 \
     do {                                                                          \

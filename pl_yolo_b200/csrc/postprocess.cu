@@ -417,8 +417,10 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     const size_t smem = nms_group_smem_bytes(cap, np.fast_cap, max_det, NT);
     PLYOLO_REQUIRE(smem <= 190 * 1024, "nms working set (%zu B) exceeds shared memory", smem);
     cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    record_stage_event(1, stream);
     nms_group_kernel<<<dim3(kGroups, B), kNmsThreads, smem, stream>>>(np);
     PLYOLO_CHECK_LAUNCH("nms_group_kernel");
+    record_stage_event(2, stream);
     return PLYOLO_OK;
 }
 
@@ -440,6 +442,7 @@ static int launch_score(const ScoreParams &sp, cudaStream_t stream) {
         return PLYOLO_ERR_CUDA;
     }
     const size_t tile_b = (size_t)kPpTile * sp.ch * sizeof(float);
+    record_stage_event(0, stream);
     if (sp.bulk_ok) {
         const size_t smem = tile_b * kStages;
         cudaFuncSetAttribute(score_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -775,11 +775,14 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     const size_t bm = (2 * (size_t)((A + 31) / 32) + 1) * sizeof(unsigned);
     PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
     if (bm > 40 * 1024) cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm);
+    record_stage_event(0, st);
     simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
+    record_stage_event(1, st);
     cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));
     simota_match_kernel<<<dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), kMatchThreads, sizeof(MatchShared), st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_match_kernel");
+    record_stage_event(2, st);
     return PLYOLO_OK;
 }
 
