@@ -1,5 +1,5 @@
 // simota.cu — SimOTA label assignment for a whole batch (yolox_loss.py:43-118, :231-370;
-// iou_loss.py:391-414).  Two launches, no host synchronisation, no [G,Nc,80] temporaries.
+// iou_loss.py:391-414).  Three launches, no host synchronisation, no [G,Nc,80] temporaries.
 //
 //  K1 simota_prep_kernel      4 CTAs per image
 //     GT count (:43), closed-form geometry prior: for every (GT, level) the in-box and in-centre
@@ -9,14 +9,16 @@
 //     quarter of the anchors: background defaults of the outputs, ordered compaction of the
 //     candidates (candidate n <-> n-th set bit, :79-82) and the gather of their corner boxes / areas
 //     (16 of the 340 bytes of each prediction row) for the IoU sweep.
-//  K2 simota_match_kernel     one CTA (16 warps) per 8 GTs of an image
-//     1. IoU of its GTs against every candidate, candidates staged through shared memory in chunks,
-//        two warps per GT with warp-resident top-10 lists (values only, :336-340; the division runs
-//        only when a pair can enter the list) -> dynamic k with ATen's reduce tree;
+//  K2a simota_sweep_kernel    32 CTAs per image: (candidate slice, quarter of the GTs)
+//     top-10 IoU values (:336-340) of every GT inside every slice; groups of 32 candidates whose
+//     union box misses the GT are skipped (their IoU is 0).
+//  K2b simota_match_kernel    one CTA (16 warps) per 8 GTs of an image
+//     1. merge of the slice lists -> dynamic k with ATen's reduce tree;
 //     2. cost (:84-108) only for the <= 25 * levels anchors that are both in-box and in-centre (every
-//        other cost carries +1e5, so the k smallest live there unless the GT is tiny): one warp per
-//        (GT, anchor) pair, 80-class BCE in ATen's CUDA reduce order (lane t adds classes t, t+32,
-//        t+64, then a halving tree);
+//        other cost carries +1e5, so the k smallest live there unless the GT is tiny), and of those
+//        only the pairs that can still be among the k smallest: a bit-exact lower bound (positive BCE
+//        leaf + IoU term) prunes the expensive 80-class sweep (one warp per pair, ATen's CUDA reduce
+//        order: lane t adds classes t, t+32, t+64, then a halving tree);
 //     3. k smallest (cost, anchor) per GT -> per-anchor match count / tentative match by atomics;
 //        anchors claimed twice are resolved right away by the argmin of the cost over ALL GTs
 //        (:352-356, quirk Q4);
@@ -33,8 +35,11 @@ constexpr int kPrepSplit = 4;     // CTAs per image in the prep kernel
 constexpr int kGtPerCta = 8;      // GTs per CTA in the match kernel
 constexpr int kMatchWarps = 16;   // two per GT during the IoU sweep
 constexpr int kMatchThreads = kMatchWarps * 32;
-constexpr int kChunk = 2048;      // candidates staged per pass
+constexpr int kSweepSplit = 8;   // CTAs per image in the IoU sweep: each takes one slice of the candidates
+constexpr int kSweepThreads = 256;
+constexpr int kSweepGtSplit = 4;  // ... and one quarter of the image's GTs (grid.x = kSweepSplit * kSweepGtSplit)
 constexpr int kMaxBoth = 36 * PLYOLO_MAX_LEVELS;  // 5x5 centre cells per level (6x6 if an edge rounds outward)
+constexpr int kExtraEval = 4;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
 constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
 
 struct SimParams {
@@ -58,6 +63,8 @@ struct SimParams {
     int *res_g;           // [B,A]  conflict resolution: argmin GT ...
     float *res_iou;       // [B,A]  ... and its IoU
     short *rect;          // [B,Lmax,n_levels,8] in-box x0,x1,y0,y1 | in-centre x0,x1,y0,y1 (inclusive)
+    float *top_part;      // [B,Lmax,kSweepSplit,10] the 10 largest IoUs of every GT inside every candidate slice
+    long long *prof;      // debug: [B][gridDim.x][16] phase timestamps of the match kernel, or null
 };
 
 // ---- arithmetic shared by the three kernels ------------------------------------------------
@@ -441,10 +448,100 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
     __syncwarp();
 }
 
+// ---- K2a: IoU sweep ---------------------------------------------------------------------------
+// Grid (kSweepSplit, B).  The CTA stages ONE slice of the image's candidates (corner boxes, areas, the union
+// box of every group of 32 consecutive candidates) and its warps walk the image's GTs: a GT only visits the
+// groups whose union box it overlaps (the others have IoU 0 throughout) and keeps the 10 largest IoUs of the
+// slice in a warp-resident list (values only, :336-340; bboxes_iou with xyxy=False, iou_loss.py:400-414, the
+// division runs only when a pair can enter the list).  The match kernel merges the kSweepSplit lists.
+__global__ void __launch_bounds__(kSweepThreads) simota_sweep_kernel(const SimParams p, const int slice_cap) {
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    float4 *cbox = reinterpret_cast<float4 *>(sweep_smem);             // [slice_cap]
+    float4 *gbox = cbox + slice_cap;                                   // [slice_cap / 32]
+    float *carea = reinterpret_cast<float *>(gbox + slice_cap / 32);   // [slice_cap]
+    const int c = blockIdx.x % kSweepSplit, gq4 = blockIdx.x / kSweepSplit, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
+    if (G == 0 || Nc == 0) return;
+    const int g_per = (G + kSweepGtSplit - 1) / kSweepGtSplit;
+    const int g_lo = gq4 * g_per, g_hi = min(G, g_lo + g_per);
+    if (g_lo >= g_hi) return;
+    __shared__ int s_next_gt;
+    if (tid == 0) s_next_gt = g_lo;
+    const int per = (((Nc + kSweepSplit - 1) / kSweepSplit) + 31) & ~31;  // slice length, whole groups
+    const int n0 = c * per, cn = max(0, min(per, Nc - n0));
+    const float4 *cb = p.cand_box + (size_t)b * p.A + n0;
+    const float *car = p.cand_area + (size_t)b * p.A + n0;
+    for (int i = tid; i < cn; i += kSweepThreads) {
+        cbox[i] = cb[i];
+        carea[i] = car[i];
+    }
+    __syncthreads();
+    const int ngroups = (cn + 31) >> 5;
+    for (int gq = warp; gq < ngroups; gq += kSweepThreads / 32) {
+        const int n = gq * 32 + lane;
+        float4 u = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+        if (n < cn) u = cbox[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u.x = fminf(u.x, __shfl_xor_sync(0xffffffffu, u.x, o));
+            u.y = fminf(u.y, __shfl_xor_sync(0xffffffffu, u.y, o));
+            u.z = fmaxf(u.z, __shfl_xor_sync(0xffffffffu, u.z, o));
+            u.w = fmaxf(u.w, __shfl_xor_sync(0xffffffffu, u.w, o));
+        }
+        if (lane == 0) gbox[gq] = u;
+    }
+    __syncthreads();
+    for (;;) {  // the warps take the CTA's GTs dynamically: the work per GT varies with its overlaps
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&s_next_gt, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= g_hi) break;
+        const float *L = p.labels + ((size_t)b * p.Lmax + g) * 5;
+        const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
+        const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
+        const float area_a = gw * gh;
+        // lists start at +0: a pair that does not overlap has IoU (+/-)0 and can never displace anything
+        float top = 0.f, thresh = 0.f;
+        for (int q0 = 0; q0 < ngroups; q0 += 32) {
+            bool h = false;
+            if (q0 + lane < ngroups) {
+                const float4 u = gbox[q0 + lane];
+                h = fmaxf(g_x1, u.x) < fminf(g_x2, u.z) && fmaxf(g_y1, u.y) < fminf(g_y2, u.w);
+            }
+            unsigned hit = __ballot_sync(0xffffffffu, h);
+            while (hit) {
+                const int gq = q0 + __ffs(hit) - 1;
+                hit &= hit - 1;
+                const int n = gq * 32 + lane;
+                float v = 0.f;
+                if (n < cn) {
+                    const float4 cc = cbox[n];
+                    const float tlx = fmaxf(g_x1, cc.x), tly = fmaxf(g_y1, cc.y);
+                    const float brx = fminf(g_x2, cc.z), bry = fminf(g_y2, cc.w);
+                    if (tlx < brx && tly < bry) {  // en == 1
+                        const float area_i = (brx - tlx) * (bry - tly);
+                        const float den = (area_a + carea[n]) - area_i;
+                        if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, v > thresh);
+                if (m) {
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        top_insert(top, __shfl_sync(0xffffffffu, v, j), lane);
+                    }
+                    thresh = __shfl_sync(0xffffffffu, top, 9);
+                }
+            }
+        }
+        if (lane < 10) p.top_part[(((size_t)b * p.Lmax + g) * kSweepSplit + c) * 10 + lane] = top;
+    }
+}
+
 // ---- K2 ------------------------------------------------------------------------------------
 struct MatchShared {
-    float4 cbox[kChunk];
-    float carea[kChunk];
     int anchor[kGtPerCta][kMaxBoth];
     float cost[kGtPerCta][kMaxBoth];
     float iou[kGtPerCta][kMaxBoth];
@@ -452,7 +549,9 @@ struct MatchShared {
     float terms[kMatchWarps][96];
     int conf[kMaxConf];
     int k[kGtPerCta], nb[kGtPerCta];
-    int nconf, last;
+    int nconf, last, n_eval;
+    unsigned short elist[kGtPerCta * kMaxBoth];    // (GT, anchor slot) pairs whose exact cost is wanted
+    unsigned char state[kGtPerCta][kMaxBoth];      // 0 = lower bound only, 1 = queued, 2 = exact cost known
 };
 
 __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimParams p) {
@@ -475,6 +574,9 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     // ATen picks a 64-wide block for sum(-1) when the [G,Nc] output has fewer than 16 elements (and C >= 64)
     const bool wide = (long long)G * Nc < 16 && p.C >= 64;
     if (tid == 0) sh.nconf = 0;
+    long long *prof = p.prof ? p.prof + ((size_t)b * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define SPROF(slot) do { if (prof) { __syncthreads(); if (tid == 0) prof[slot] = clock64(); } } while (0)
+    SPROF(0);
 
     // ---- 0. anchors both in-box and in-centre of every GT of the CTA (ascending anchor order; closed form from
     // the rectangles) and an L2 prefetch of their prediction rows: the IoU sweep below hides the DRAM latency
@@ -505,55 +607,25 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
         if (lane == 0) sh.nb[gi] = nb;
     }
 
-    // ---- 1. top-10 IoU values over all candidates (iou_loss.py:400-414 with xyxy=False; GT-side operands
-    // hoisted).  Lists start at +0: a pair that does not overlap has IoU (+/-)0 and can never displace
-    // anything; the division runs only when the quotient could exceed the current 10th value.
-    const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
-    const float area_a = gw * gh;
-    float top = 0.f, thresh = 0.f;
-    for (int c0 = 0; c0 < Nc; c0 += kChunk) {
-        const int cn = min(kChunk, Nc - c0);
-        __syncthreads();  // the previous chunk is no longer read
-        for (int i = tid; i < cn; i += kMatchThreads) {
-            sh.cbox[i] = cb[c0 + i];
-            sh.carea[i] = car[c0 + i];
-        }
-        __syncthreads();
-        if (live) {
-            const int per = (((cn + 1) >> 1) + 31) & ~31;
-            const int n_lo = half * per, n_hi = min(cn, n_lo + per);
-            for (int n0 = n_lo; n0 < n_hi; n0 += 32) {
-                const int n = n0 + lane;
-                float v = 0.f;
-                if (n < n_hi) {
-                    const float4 c = sh.cbox[n];
-                    const float tlx = fmaxf(g_x1, c.x), tly = fmaxf(g_y1, c.y);
-                    const float brx = fminf(g_x2, c.z), bry = fminf(g_y2, c.w);
-                    if (tlx < brx && tly < bry) {  // en == 1
-                        const float area_i = (brx - tlx) * (bry - tly);
-                        const float den = (area_a + sh.carea[n]) - area_i;
-                        if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
-                    }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, v > thresh);
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    top_insert(top, __shfl_sync(0xffffffffu, v, j), lane);
-                }
-                thresh = __shfl_sync(0xffffffffu, top, 9);
-            }
-        }
-    }
-    if (lane < 10) sh.top[warp][lane] = top;
-    __syncthreads();
+    SPROF(1);
+    // ---- 1. the 10 largest IoUs of every GT: merge of the kSweepSplit slice lists (values only, :336-340)
+    SPROF(2);
     if (half == 0 && live) {
-        const float mine = lane < 10 ? sh.top[warp + kGtPerCta][lane] : 0.f;  // the partner warp's 10 values
-        for (int j = 0; j < 10; ++j) {
-            const float x = __shfl_sync(0xffffffffu, mine, j);
-            if (x > thresh) {
-                top_insert(top, x, lane);
-                thresh = __shfl_sync(0xffffffffu, top, 9);
+        float sv[3];  // 80 slice values, up to 3 per lane
+        const float *tp = p.top_part + ((size_t)b * p.Lmax + g) * kSweepSplit * 10;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) sv[u] = (lane + 32 * u < kSweepSplit * 10) ? __ldg(tp + lane + 32 * u) : -1.f;
+        float top = 0.f;  // lane i < 10: i-th largest
+        for (int r = 0; r < 10; ++r) {
+            float m = fmaxf(sv[0], fmaxf(sv[1], sv[2]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == r) top = fmaxf(m, 0.f);
+            // remove ONE instance of the maximum (equal values of different candidates are separate entries)
+            const bool mine = sv[0] == m || sv[1] == m || sv[2] == m;
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            if (who && lane == __ffs(who) - 1) {
+                if (sv[0] == m) sv[0] = -1.f; else if (sv[1] == m) sv[1] = -1.f; else sv[2] = -1.f;
             }
         }
         // dynamic k = clamp(int(sum of the top min(10, Nc)), 1) with ATen's reduce tree (:336-340)
@@ -577,44 +649,134 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     }
     __syncthreads();
 
-    // ---- 2. cost of the in-both anchors (:84-108), one warp per (GT, anchor) pair.  The pairs of the CTA's GTs
-    // form one flat list; every warp walks it with stride 16 and loads the NEXT pair's prediction row (DRAM:
-    // 340 of the row's bytes, three coalesced requests) before it evaluates the current one.
-    {
-        int pbase[kGtPerCta + 1];
-        pbase[0] = 0;
+    // ---- 2. cost of the in-both anchors (:84-108).  Only the k smallest costs of a GT matter, and
+    //   cost = fl(fl(cls + 3 L_iou) + 0),  cls = ATen-ordered sum of 80 non-negative BCE leaves, one of them
+    //   pos = -max(log p[gt class], -100):  every fp32 addition of non-negatives is monotone, so
+    //   lb = fl(fl(pos + 3 L_iou) + 0) <= cost, bit for bit.
+    // (a) lb for every pair, one thread each (6 floats of the row);  (b) exact cost — one warp per pair, the
+    // expensive 80-class sweep — for the k pairs of smallest lb per GT;  (c) with U = the largest of those
+    // exact costs, exact cost for every pair with lb <= U: all others cost more than k pairs already do.
+    // The selection (3.) then runs over the exactly known costs only.
+    SPROF(3);
+    int pbase[kGtPerCta + 1];
+    pbase[0] = 0;
 #pragma unroll
-        for (int q = 0; q < kGtPerCta; ++q) pbase[q + 1] = pbase[q] + sh.nb[q];
-        const int npairs = pbase[kGtPerCta];
-        auto locate = [&](const int t, int &q, int &i) {
-            q = 0;
-            int base = 0;
+    for (int q = 0; q < kGtPerCta; ++q) pbase[q + 1] = pbase[q] + sh.nb[q];
+    const int npairs = pbase[kGtPerCta];
+    for (int t = tid; t < npairs; t += kMatchThreads) {
+        int q = 0, base = 0;
 #pragma unroll
-            for (int u = 1; u < kGtPerCta; ++u)
-                if (t >= pbase[u]) { q = u; base = pbase[u]; }
-            i = t - base;
-        };
+        for (int u = 1; u < kGtPerCta; ++u)
+            if (t >= pbase[u]) { q = u; base = pbase[u]; }
+        const int i = t - base;
+        const float *row = p.preds + ((size_t)b * p.A + sh.anchor[q][i]) * p.ch;
+        const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
+        const int qc = (int)Lq[0];
+        float pos = 0.f;
+        if (qc >= 0 && qc < p.C) pos = pos_term(sqrtf(sigmoid_ref(__ldg(row + 5 + qc)) * sigmoid_ref(__ldg(row + 4))));
+        const float iou = pair_iou(Lq[1], Lq[2], Lq[3], Lq[4], load_box(row));
+        const float liou = -logf(iou + 1e-8f);
+        sh.cost[q][i] = (pos + 3.0f * liou) + 0.0f;
+        sh.iou[q][i] = iou;
+        sh.state[q][i] = 0;
+    }
+    if (tid == 0) sh.n_eval = 0;
+    __syncthreads();
+    // exact cost of every queued pair: the warps walk the list with stride 16, loading the NEXT pair's
+    // prediction row (three coalesced requests) before evaluating the current one
+    auto evaluate_queued = [&]() {
+        const int ne = sh.n_eval;
         RawRow cur, nxt;
         int q = 0, i = 0;
-        if (warp < npairs) {
-            locate(warp, q, i);
+        if (warp < ne) {
+            q = sh.elist[warp] / kMaxBoth; i = sh.elist[warp] % kMaxBoth;
             load_row(p.preds + ((size_t)b * p.A + sh.anchor[q][i]) * p.ch, p.C, lane, cur);
         }
-        for (int t = warp; t < npairs; t += kMatchWarps) {
+        for (int t = warp; t < ne; t += kMatchWarps) {
             int qn = 0, in_ = 0;
-            const bool more = t + kMatchWarps < npairs;
+            const bool more = t + kMatchWarps < ne;
             if (more) {
-                locate(t + kMatchWarps, qn, in_);
+                qn = sh.elist[t + kMatchWarps] / kMaxBoth; in_ = sh.elist[t + kMatchWarps] % kMaxBoth;
                 load_row(p.preds + ((size_t)b * p.A + sh.anchor[qn][in_]) * p.ch, p.C, lane, nxt);
             }
             const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
             float iou;
             const float c = pair_cost_row(p, cur, Lq[1], Lq[2], Lq[3], Lq[4], (int)Lq[0], true, wide, lane, sh.terms[warp], &iou);
-            if (lane == 0) { sh.cost[q][i] = c; sh.iou[q][i] = iou; }
+            if (lane == 0) { sh.cost[q][i] = c; sh.state[q][i] = 2; }
             if (more) { cur = nxt; q = qn; i = in_; }
+        }
+    };
+    SPROF(4);
+    // (b) queue the k smallest lower bounds of every GT (ties -> lower slot, like the final selection)
+    if (half == 0 && sh.nb[gi] > 0) {
+        const int nb = sh.nb[gi], take = min(sh.k[gi] + kExtraEval, nb);  // a few more than k: a tighter U below
+        for (int r = 0; r < take; ++r) {
+            unsigned long long best = ~0ull;
+            for (int i = lane; i < nb; i += 32)
+                if (sh.state[gi][i] == 0) {
+                    const unsigned long long key = ((unsigned long long)float_ordered(sh.cost[gi][i]) << 32) | (unsigned)i;
+                    best = key < best ? key : best;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other < best ? other : best;
+            }
+            if (lane == 0) {
+                const int i = (int)(best & 0xffffffffu);
+                sh.state[gi][i] = 1;
+                sh.elist[atomicAdd(&sh.n_eval, 1)] = (unsigned short)(gi * kMaxBoth + i);
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
+    SPROF(5);
+    evaluate_queued();
+    __syncthreads();
+    SPROF(6);
+    if (prof && tid == 0) prof[12] = sh.n_eval;
+    if (tid == 0) sh.n_eval = 0;
+    __syncthreads();
+    // (c) everything whose lower bound does not exceed the largest exact cost found so far
+    if (half == 0 && sh.nb[gi] > 0) {
+        const int nb = sh.nb[gi], kk = min(sh.k[gi], nb);
+        // U = the kk-th smallest exact cost known so far (>= the true kk-th smallest cost of the GT)
+        unsigned umax = 0u, floor_ = 0u;
+        bool first = true;
+        for (int r = 0; r < kk; ++r) {
+            unsigned long long best = ~0ull;  // smallest (cost, slot) above the previous pick
+            for (int i = lane; i < nb; i += 32)
+                if (sh.state[gi][i] == 2) {
+                    const unsigned long long key = ((unsigned long long)float_ordered(sh.cost[gi][i]) << 32) | (unsigned)i;
+                    const unsigned long long prev = ((unsigned long long)umax << 32) | floor_;
+                    if ((first || key > prev) && key < best) best = key;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other < best ? other : best;
+            }
+            umax = (unsigned)(best >> 32);
+            floor_ = (unsigned)(best & 0xffffffffu);
+            first = false;
+        }
+        for (int i = lane; i < nb; i += 32)
+            if (sh.state[gi][i] == 0) {
+                if (float_ordered(sh.cost[gi][i]) <= umax) {
+                    sh.state[gi][i] = 1;
+                    sh.elist[atomicAdd(&sh.n_eval, 1)] = (unsigned short)(gi * kMaxBoth + i);
+                } else {
+                    sh.cost[gi][i] = __int_as_float(0x7fc00000);  // cannot be among the k smallest: out of the selection
+                }
+            }
+    }
+    __syncthreads();
+    SPROF(7);
+    evaluate_queued();
+    __syncthreads();
+    SPROF(8);
+    if (prof && tid == 0) { prof[13] = sh.n_eval; prof[14] = npairs; }
 
     // ---- 3. per GT (first 8 warps): k smallest (cost, anchor); ties -> lowest anchor index (stable sort, :342)
     auto push_conflict = [&](const int a) {
@@ -680,9 +842,11 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
 
     // ---- resolve the conflicts this CTA created (one warp each)
     __syncthreads();
+    SPROF(9);
     const int nc = min(sh.nconf, kMaxConf);
     for (int i = warp; i < nc; i += kMatchWarps) resolve_conflict(p, b, sh.conf[i], G, wide, sh.terms[warp]);
 
+    SPROF(10);
     // ---- 4. the last CTA of the image to finish patches the resolved matches over the tentative ones
     __threadfence();
     __syncthreads();
@@ -698,7 +862,11 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
         }
         if (tid == 0) p.num_fg[b] = __ldcg(p.meta + b * 8 + 3);  // :358
     }
+    SPROF(11);
+#undef SPROF
 }
+
+static thread_local long long *g_sim_prof = nullptr;
 
 static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, unsigned char *base) {
     size_t off = 0;
@@ -712,7 +880,9 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
     const size_t o_sc = take((size_t)B * A * sizeof(unsigned));
     const size_t o_sm = take((size_t)B * A * sizeof(unsigned));
     const size_t o_rect = take((size_t)B * Lmax * n_levels * 8 * sizeof(short));
+    const size_t o_top = take((size_t)B * Lmax * kSweepSplit * 10 * sizeof(float));
     if (p) {
+        p->top_part = reinterpret_cast<float *>(base + o_top);
         p->meta = reinterpret_cast<int *>(base + o_meta);
         p->conf_list = reinterpret_cast<int *>(base + o_sl);
         p->res_iou = reinterpret_cast<float *>(base + o_ri);
@@ -727,6 +897,10 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
 }
 
 }  // namespace plyolo
+
+// debug hook (not part of include/plyolo.h): device buffer [B][ceil(Lmax/8)][16] of int64 for the match kernel's
+// phase timestamps (adds barriers: timing only), null switches it off
+extern "C" void plyolo_debug_simota_profile(void *device_buf) { plyolo::g_sim_prof = static_cast<long long *>(device_buf); }
 
 extern "C" size_t plyolo_simota_workspace_bytes(int B, int A, int Lmax, int n_levels) {
     if (B < 1 || A < 1 || Lmax < 1 || n_levels < 1) return 0;
@@ -771,6 +945,7 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     p.preds = preds; p.labels = labels; p.B = B; p.A = A; p.C = C; p.ch = 5 + C; p.Lmax = Lmax; p.n_levels = n_levels;
     p.fg_mask = fg_mask; p.matched_gt = matched_gt; p.matched_iou = matched_iou; p.num_fg = num_fg; p.num_gt = num_gt;
     sim_ws_layout(B, A, Lmax, n_levels, &p, static_cast<unsigned char *>(workspace));
+    p.prof = g_sim_prof;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bm = (2 * (size_t)((A + 31) / 32) + 1) * sizeof(unsigned);
     PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
@@ -778,6 +953,13 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     record_stage_event(0, st);
     simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
+    const int slice_cap = ((((A + kSweepSplit - 1) / kSweepSplit) + 31) & ~31) + 32;
+    const size_t sweep_smem = (size_t)slice_cap * 20 + (size_t)(slice_cap / 32) * 16;
+    PLYOLO_REQUIRE(sweep_smem <= 200 * 1024, "A=%d too large for the IoU sweep's candidate slice", A);
+    if (sweep_smem > 48 * 1024)
+        cudaFuncSetAttribute(simota_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
+    simota_sweep_kernel<<<dim3(kSweepSplit * kSweepGtSplit, B), kSweepThreads, sweep_smem, st>>>(p, slice_cap);
+    PLYOLO_CHECK_LAUNCH("simota_sweep_kernel");
     record_stage_event(1, st);
     cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));
     simota_match_kernel<<<dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), kMatchThreads, sizeof(MatchShared), st>>>(p);
