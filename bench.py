@@ -39,6 +39,7 @@ CONF, NMS = 0.01, 0.65
 BYTES_DECODE_NMS = A * 85 * 4 + 300 * 6 * 4 + 4   # 2 863 204 B / image
 BYTES_SIMOTA = A * 85 * 4 + A * 9 + 8              # + 20 * G, SURVEY.md §8d
 N_SETS = 4
+WORKLOAD = "YOLOX-s 640x640 batch 32 decode + postprocess(conf 0.01, nms 0.65) [BASELINE configs[1]]"
 
 
 def traffic_bytes(kernel: str):
@@ -164,8 +165,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLOX-s 640x640 batch 32 decode + postprocess(conf 0.01, nms 0.65), reference op chain on host CPU",
-                   "batch": BATCH, "anchors": A, "classes": C},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "anchors": A, "classes": C,
+                   "note": "reference op chain (torch/torchvision CPU kernels) on the host cores, rank 0 only"},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "%d steps x full batch of 32 images; torch %s / torchvision op-for-op replay of the reference "
                                    "(oracle/torch_ops_replay.py, bit-identical to the real reference on CPU)" % (args.steps, torch.__version__),
@@ -220,6 +221,8 @@ def main():
         with torch.cuda.stream(stream):
             for i in range(W):
                 run_step(i)
+            if finish is not None:
+                finish()  # warm-up of the exchange too (NCCL communicator set-up is not part of a step)
             barrier()
             l0 = _lib.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -411,7 +414,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "YOLOX-s 640x640 batch 32 fused decode + postprocess(conf 0.01, nms 0.65) [BASELINE configs[1]]",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH, "anchors": A, "classes": C, "dets_per_image": dets_per_img,
                        "launch": mode, "l2": "4 input sets rotated (366 MB > 126 MB L2)",
                        "exchange": "none" if world == 1 else "one NCCL all-gather of the last 4 steps' padded detections + counts inside the timed region"},
