@@ -17,6 +17,10 @@
 //   candidates against the kept list (<= max_det, early exit: output order == score order == sweep
 //   order) with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division;
 //   see `suppresses`).
+#include <cstring>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace plyolo {
@@ -57,6 +61,7 @@ struct ScoreParams {
     float conf_thr;
     int bulk_ok;
     CandWs ws;
+    long long *prof;  // debug: [gridDim.x][kConsumers][8] accumulated cycles per consumer phase, or null
 };
 
 // per consumer group (128 threads = one tile at a time) scratch
@@ -100,9 +105,19 @@ __device__ __forceinline__ void group_barrier(const int bar_id) {
 // Scores one staged tile (128 threads, `tid` in [0,128), barrier `bar_id`).  `tile` is read-only here; after
 // the call returns the group no longer needs it IF `release` was invoked (it is called once, by every thread,
 // right after the last read of the tile).
+#define TPROF(slot)                                             \
+    do {                                                        \
+        if (acc && tid == 0) {                                  \
+            const long long now__ = clock64();                  \
+            acc[slot] += now__ - tlast;                         \
+            tlast = now__;                                      \
+        }                                                       \
+    } while (0)
+
 template <bool FUSED, typename Release>
 __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *tile, const TileCoord tc, const int tid,
-                                           const int bar_id, TileShared &sh, Release release) {
+                                           const int bar_id, TileShared &sh, Release release, long long *acc = nullptr,
+                                           long long tlast = 0) {
     const int ch = p.ch, b = tc.b, l = tc.l, a0 = tc.a0, cnt = tc.cnt;
     const int lane = tid & 31, warp = tid >> 5;
     bool pass = false;
@@ -123,21 +138,25 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         if (tid < cnt) {
             const float so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
             if (so >= p.conf_thr) {
-                // one branch-free sweep, 4 independent chains (classes = chain mod 4): largest and second largest
-                // raw logit and the first index of the largest
+                // one branch-free sweep, 4 independent chains (classes = chain mod 4: the loads and the dependent
+                // min/max of different chains overlap; 8 chains measured slower): largest and second largest raw
+                // logit and the first index of the largest
+                constexpr int NCH = 4;
                 const float *col = tile + 5 * kPpTile + tid;
-                float m1[4], m2[4];
-                int i1[4];
+                float m1[NCH], m2[NCH];
+                int i1[NCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { m1[u] = -3.0e38f; m2[u] = -3.0e38f; i1[u] = 0; }
+                for (int u = 0; u < NCH; ++u) { m1[u] = -3.0e38f; m2[u] = -3.0e38f; i1[u] = 0; }
                 int c = 0;
-                for (; c + 3 < p.C; c += 4) {
+                for (; c + NCH - 1 < p.C; c += NCH) {
+                    float x[NCH];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float x = col[(c + u) * kPpTile];
-                        m2[u] = fmaxf(m2[u], fminf(x, m1[u]));
-                        i1[u] = x > m1[u] ? c + u : i1[u];
-                        m1[u] = fmaxf(m1[u], x);
+                    for (int u = 0; u < NCH; ++u) x[u] = col[(c + u) * kPpTile];
+#pragma unroll
+                    for (int u = 0; u < NCH; ++u) {
+                        m2[u] = fmaxf(m2[u], fminf(x[u], m1[u]));
+                        i1[u] = x[u] > m1[u] ? c + u : i1[u];
+                        m1[u] = fmaxf(m1[u], x[u]);
                     }
                 }
                 for (; c < p.C; ++c) {
@@ -147,7 +166,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
                     m1[0] = fmaxf(m1[0], x);
                 }
 #pragma unroll
-                for (int u = 1; u < 4; ++u) {  // fold chain u into chain 0
+                for (int u = 1; u < NCH; ++u) {  // fold chain u into chain 0
                     m2[0] = fmaxf(fmaxf(m2[0], m2[u]), fminf(m1[0], m1[u]));
                     i1[0] = m1[u] > m1[0] ? i1[u] : (m1[u] == m1[0] ? min(i1[0], i1[u]) : i1[0]);
                     m1[0] = fmaxf(m1[0], m1[u]);
@@ -197,7 +216,9 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         pass = conf >= p.conf_thr;
         box = make_float4(r[0], r[1], r[2], r[3]);
     }
+    TPROF(2);
     release();  // last read of the tile is done (every thread calls it)
+    TPROF(3);
 
     // ---- order-preserving compaction into the tile's slots (postprocess.py:23 keeps anchor order)
     const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -216,6 +237,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
     if (lane == 0) sh.w_max[warp] = cm;
     group_barrier(bar_id);
+    TPROF(4);
     int base = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kPpTile / 32; ++w) {
@@ -247,6 +269,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         atomicMax(reinterpret_cast<unsigned *>(&ctr[kGroups]), float_ordered(mx));
     }
     group_barrier(bar_id);
+    TPROF(5);
     if (pass) {
         int pos = sh.g_base[grp] + __popc(gm & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) pos += sh.g_wcnt[w][grp];
@@ -261,6 +284,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
             }
         }
     }
+    TPROF(6);
 }
 
 // ---- one CTA per tile, plain loads: the fallback for unaligned inputs (no 16-byte alignment for bulk copies)
@@ -290,7 +314,8 @@ __global__ void __launch_bounds__(kPpTile) score_kernel_simple(const ScoreParams
 // chains, barriers, the bucket atomics) overlaps the next tiles' loads and compute.
 constexpr int kStages = 4;
 constexpr int kConsumers = 3;
-constexpr int kScoreThreads = 32 + kPpTile * kConsumers;
+constexpr int kProducers = 2;  // producer warps (FUSED: each copies half of the channel rows)
+constexpr int kScoreThreads = 32 * kProducers + kPpTile * kConsumers;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -304,8 +329,24 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one 2-D tensor map per FPN level: dim0 = the H*W anchors of a channel plane (contiguous), dim1 = the
+// B * (5+C) planes; a tile is the box (128 anchors, 5+C planes) at (a0, b * (5+C)) — ONE request to the TMA
+// engine per tile; anchors past the end of the level are zero-filled
+struct TmapPack {
+    CUtensorMap m[PLYOLO_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, const int c0, const int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
 template <bool FUSED>
-__global__ void __launch_bounds__(kScoreThreads, 1) score_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const int use_tmap) {
     extern __shared__ __align__(128) float stages[];  // [kStages][ch * 128]
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
     __shared__ TileShared sh[kConsumers];
@@ -313,25 +354,39 @@ __global__ void __launch_bounds__(kScoreThreads, 1) score_kernel(const ScorePara
     const int stage_floats = p.ch * kPpTile;
     const int total = p.NT * p.B;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], FUSED ? 32 : 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], (FUSED && !use_tmap) ? 32 * kProducers : 1); mbar_init(&empty_bar[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
-    if (warp == 0) {
-        // ---- producer
-        int seq = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++seq) {
+    // the CTA's seq-th tile: adjacent tiles come in pairs, so that one CTA asks for 1 KB of every channel plane
+    // back to back (DRAM page locality)
+    auto tile_of = [&](const int seq) { return 2 * ((int)blockIdx.x + (seq >> 1) * (int)gridDim.x) + (seq & 1); };
+    if (warp < kProducers) {
+        // ---- producers
+        if ((!FUSED || use_tmap) && warp > 0) return;  // one request per tile: one warp is plenty
+        for (int seq = 0;; ++seq) {
+            const int t = tile_of(seq);
+            if (t >= total) break;
             const int s = seq % kStages, k = seq / kStages;
             if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
             const TileCoord tc = tile_coord<FUSED>(p, t / p.NT, t % p.NT);
             float *dst = stages + (size_t)s * stage_floats;
+            if (FUSED && use_tmap) {
+                if (lane == 0) {
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(p.ch * kPpTile * 4));  // the whole box, zero fill included
+                    tma_load_2d(dst, &tmaps.m[tc.l], tc.a0, tc.b * p.ch, &full_bar[s]);
+                }
+                continue;
+            }
             if (FUSED) {
                 if (lane * 4 < tc.cnt) {  // cnt is a multiple of 4 (bulk_ok)
-                    const float *g = tc.src + lane * 4;
-                    float *d = dst + lane * 4;
+                    const int c_per = (p.ch + kProducers - 1) / kProducers;
+                    const int c_lo = warp * c_per, c_hi = min(p.ch, c_lo + c_per);
                     const size_t hw = (size_t)p.lv.hw[tc.l];
-#pragma unroll 5
-                    for (int c = 0; c < p.ch; ++c) cp_async16(d + c * kPpTile, g + c * hw);
+                    const float *g = tc.src + lane * 4 + c_lo * hw;
+                    float *d = dst + lane * 4 + c_lo * kPpTile;
+#pragma unroll 4
+                    for (int c = c_lo; c < c_hi; ++c, g += hw, d += kPpTile) cp_async16(d, g);
                 }
                 cp_async_arrive(&full_bar[s]);
             } else if (lane == 0) {
@@ -341,22 +396,26 @@ __global__ void __launch_bounds__(kScoreThreads, 1) score_kernel(const ScorePara
         }
     } else {
         // ---- consumers
-        const int grp = (warp - 1) >> 2, gtid = tid - 32 - grp * kPpTile;
+        const int grp = (warp - kProducers) >> 2, gtid = tid - 32 * kProducers - grp * kPpTile;
         for (int seq = grp;; seq += kConsumers) {
-            const int t = blockIdx.x + seq * gridDim.x;
+            const int t = tile_of(seq);
             if (t >= total) break;
             const int s = seq % kStages, k = seq / kStages;
             // Stage s is consumed by a different group every time (3 groups, 4 stages), and an mbarrier wait only
             // knows the phase PARITY: waiting for fill k while fill k-1 has not even landed would return at
             // once.  The stage's release k-1 (which implies fill k-1 completed and was consumed; release k-2 is
             // already implied by this group's own progress) is therefore awaited first.
+            long long *acc = p.prof ? p.prof + ((size_t)blockIdx.x * kConsumers + grp) * 8 : nullptr;
+            const long long tw0 = acc ? clock64() : 0;
             if (k > 0) mbar_wait(&empty_bar[s], (k - 1) & 1);
             mbar_wait(&full_bar[s], k & 1);
+            const long long tw1 = acc ? clock64() : 0;
+            if (acc && gtid == 0) { acc[1] += tw1 - tw0; acc[7] += 1; }
             const TileCoord tc = tile_coord<FUSED>(p, t / p.NT, t % p.NT);
             score_tile<FUSED>(p, stages + (size_t)s * stage_floats, tc, gtid, 1 + grp, sh[grp], [&] {
                 group_barrier(1 + grp);
                 if (gtid == 0) mbar_arrive(&empty_bar[s]);
-            });
+            }, acc, tw1);
         }
     }
 }
@@ -368,6 +427,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) score_kernel(const ScorePara
 namespace plyolo {
 
 static thread_local long long *g_nms_prof = nullptr;
+static thread_local long long *g_score_prof = nullptr;
 
 static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t off = 0;
@@ -447,7 +507,39 @@ static int launch_score(const ScoreParams &sp, cudaStream_t stream) {
         const size_t smem = tile_b * kStages;
         cudaFuncSetAttribute(score_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int total = sp.NT * sp.B, sms = sm_count();
-        score_kernel<FUSED><<<total < sms ? total : sms, kScoreThreads, smem, stream>>>(sp);
+        TmapPack pack;
+        memset(&pack, 0, sizeof(pack));
+        int use_tmap = 0;
+        if (FUSED) {
+            // 2-D tensor maps over the head maps: [B * (5+C) planes][H*W anchors], box = (128 anchors, 5+C planes)
+            typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static thread_local EncodeFn encode = nullptr;
+            static thread_local bool looked_up = false;
+            if (!looked_up) {
+                looked_up = true;
+                void *fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                    qres == cudaDriverEntryPointSuccess)
+                    encode = reinterpret_cast<EncodeFn>(fn);
+                else
+                    cudaGetLastError();
+            }
+            use_tmap = encode != nullptr && sp.ch <= 256;
+            for (int l = 0; use_tmap && l < sp.lv.n; ++l) {
+                const cuuint64_t gdim[2] = {(cuuint64_t)sp.lv.hw[l], (cuuint64_t)sp.B * sp.ch};
+                const cuuint64_t gstride[1] = {(cuuint64_t)sp.lv.hw[l] * sizeof(float)};
+                const cuuint32_t box[2] = {(cuuint32_t)kPpTile, (cuuint32_t)sp.ch};
+                const cuuint32_t estr[2] = {1, 1};
+                const CUresult r = encode(&pack.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(sp.lv.ptr[l]), gdim,
+                                          gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) use_tmap = 0;  // fall back to the cp.async producer
+            }
+        }
+        score_kernel<FUSED><<<(total + 1) / 2 < sms ? (total + 1) / 2 : sms, kScoreThreads, smem, stream>>>(sp, pack, use_tmap);
         PLYOLO_CHECK_LAUNCH("score_kernel");
     } else {
         if (tile_b > 48 * 1024) cudaFuncSetAttribute(score_kernel_simple<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_b);
@@ -479,6 +571,7 @@ static int check_post_args(int B, int A, int C, int max_nms, int max_det, int fl
 
 // debug hook (not part of include/plyolo.h): device buffer [B][16] of int64 receiving the NMS kernel's phase
 // timestamps for the calling thread's next launches; null switches it off
+extern "C" void plyolo_debug_score_profile(void *device_buf) { plyolo::g_score_prof = static_cast<long long *>(device_buf); }
 extern "C" void plyolo_debug_nms_profile(void *device_buf) { plyolo::g_nms_prof = static_cast<long long *>(device_buf); }
 
 extern "C" size_t plyolo_postprocess_workspace_bytes(int B, int A) {
@@ -501,6 +594,7 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.NT = (A + kPpTile - 1) / kPpTile;
     sp.conf_thr = (float)conf_thre;  // `tensor >= python float` compares in fp32
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (A & 3) == 0) ? 1 : 0;
+    sp.prof = nullptr;
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     rc = launch_score<false>(sp, (cudaStream_t)stream);
@@ -529,6 +623,7 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     bool bulk = true;
     for (int l = 0; l < sp.lv.n; ++l) bulk = bulk && ((uintptr_t)sp.lv.ptr[l] & 15) == 0 && (sp.lv.hw[l] & 3) == 0;
     sp.bulk_ok = bulk ? 1 : 0;
+    sp.prof = g_score_prof;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     rc = launch_score<true>(sp, (cudaStream_t)stream);
     if (rc != PLYOLO_OK) return rc;
