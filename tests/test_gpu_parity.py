@@ -406,6 +406,35 @@ def test_simota_cfg3_full_size_vs_oracle():
         assert np.array_equal(inv[b][m2], got["matched_gt"][b][fg[b]])
 
 
+def test_simota_cfg5_dense_gt_stress_vs_oracle():
+    """BASELINE cfg5 shapes at a small batch: 1280^2 (33600 anchors), 250..500 GTs per image, 40 objects per image;
+    plus the BASELINE cfg4 label layout (Lmax 120) at batch 8.  Bit-exact against the CPU oracle."""
+    heads = synth.make_heads(2, 1280, 80, 51, objects_per_image=40)
+    labels = synth.make_labels(2, 1280, 500, 80, 52, min_gt=250, max_gt=500)
+    dec, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    preds = dec.cpu().numpy()
+    got = run_simota(preds, labels, 1280)
+    o = oracle.simota(preds, labels, synth.level_shapes(1280), STRIDES)
+    assert_simota_equal(got, o, "oracle cfg5")
+    assert (got["num_gt"] >= 250).all() and (got["num_fg"] > 0).all()
+    heads = synth.make_heads(8, 640, 80, 53)
+    labels = synth.make_labels(8, 640, 120, 80, 54)
+    dec, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    preds = dec.cpu().numpy()
+    assert_simota_equal(run_simota(preds, labels, 640), oracle.simota(preds, labels, synth.level_shapes(640), STRIDES), "oracle cfg4")
+
+
+def test_decode_postprocess_cfg5_1280():
+    """BASELINE cfg5 decode + NMS: 1280^2, ~16k candidates per image -> max_nms truncation by position, general path."""
+    heads = [cu(h) for h in synth.make_heads(2, 1280, 80, 55, objects_per_image=40)]
+    d2, c2, k2 = ops.decode_postprocess_raw(heads, STRIDES, 0.01, 0.65, False, 10000, 300, 0)
+    preds, _ = ops.decode_raw(heads, STRIDES, True)
+    d1, c1, k1 = ops.postprocess_raw(preds, 0.01, 0.65, False, 10000, 300, 0)
+    assert torch.equal(c1, c2) and torch.equal(k1, k2) and torch.equal(d1, d2)
+    rd, rc = replay_dets(R.decode(heads, STRIDES, True)[0], 0.01, 0.65, False)
+    assert np.array_equal(c2.cpu().numpy(), rc) and np.array_equal(d2.cpu().numpy(), rd)
+
+
 def test_simota_adversarial_edges_vs_oracle():
     """Tiny GTs (k > #in-both -> +1e5 quantised ties), duplicates, Q3 (k >= Nc-1), dense overlaps, G=0."""
     size = 160
