@@ -127,6 +127,14 @@ int plyolo_simota_f32(const float *preds, const float *labels, int B, int A, int
 int plyolo_bboxes_iou_f32(const float *a, int na, const float *b, int nb, int xyxy, float *out,
                           plyolo_stream_t stream);
 
+/* device part of format_outputs (models/evaluators/postprocess.py:95-138; xyxy2xywh models/utils/bbox.py:58-63):
+ * rescales every detection exactly as `bboxes /= scale` does on CUDA tensors and converts to xywh.
+ *   dets [B, max_det, 6], counts [B] as returned by plyolo_postprocess_f32; inv_scales [B] fp32 =
+ *   (float)(1.0 / scale) with scale = the reference's min(val_w / img_w, val_h / img_h) in double
+ *   out  [B, max_det, 8] rows (x1, y1, x2, y2, w, h, score, class), zero padded past counts[b] */
+int plyolo_format_dets_f32(const float *dets, const int32_t *counts, const float *inv_scales, int B, int max_det,
+                           float *out, plyolo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

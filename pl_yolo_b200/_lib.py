@@ -40,6 +40,8 @@ def _declare(lib):
     lib.plyolo_simota_f32.restype = c_int
     lib.plyolo_simota_f32.argtypes = [vp, vp, c_int, c_int, c_int, c_int, ip, ip, ip, c_int, vp, vp, vp, vp, vp, vp,
                                       c_size_t, vp]
+    lib.plyolo_format_dets_f32.restype = c_int
+    lib.plyolo_format_dets_f32.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
     lib.plyolo_bboxes_iou_f32.restype = c_int
     lib.plyolo_bboxes_iou_f32.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
 

@@ -137,3 +137,42 @@ extern "C" int plyolo_decode_f32(const float *const *host_lvl, const int *hs, co
     PLYOLO_CHECK_LAUNCH("decode_kernel");
     return PLYOLO_OK;
 }
+
+// ---- format_outputs (models/evaluators/postprocess.py:95-138), device part ---------------------------
+// per detection: bboxes /= scale (in place: the VOC rows keep the rescaled corners), xyxy2xywh
+// (models/utils/bbox.py:58-63).  `tensor /= python_float` on CUDA multiplies by the reciprocal of the scalar
+// (ATen BinaryDivTrueKernel.cu, CPU-scalar fast path); measured on B200 with torch 2.11: the reciprocal is
+// taken in double and then rounded, x * (float)(1.0 / scale) — the caller passes that factor.
+namespace plyolo {
+__global__ void format_dets_kernel(const float *dets, const int32_t *counts, const float *inv_scales, int B, int max_det,
+                                   float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * max_det) return;
+    const int b = i / max_det, r = i - b * max_det;
+    float *o = out + (size_t)i * 8;
+    if (r >= counts[b]) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        return;
+    }
+    const float *d = dets + (size_t)i * 6;
+    const float inv = inv_scales[b];
+    const float x1 = d[0] * inv, y1 = d[1] * inv, x2 = d[2] * inv, y2 = d[3] * inv;
+    o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+    o[4] = x2 - x1; o[5] = y2 - y1;  // xyxy2xywh
+    o[6] = d[4]; o[7] = d[5];
+}
+}  // namespace plyolo
+
+extern "C" int plyolo_format_dets_f32(const float *dets, const int32_t *counts, const float *inv_scales, int B, int max_det,
+                                      float *out, plyolo_stream_t stream) {
+    using namespace plyolo;
+    PLYOLO_REQUIRE(dets && counts && inv_scales && out, "null pointer");
+    PLYOLO_REQUIRE(B >= 1 && max_det >= 1, "B=%d max_det=%d must be positive", B, max_det);
+    int rc = check_device();
+    if (rc != PLYOLO_OK) return rc;
+    const int n = B * max_det;
+    format_dets_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dets, counts, inv_scales, B, max_det, out);
+    PLYOLO_CHECK_LAUNCH("format_dets_kernel");
+    return PLYOLO_OK;
+}

@@ -212,6 +212,31 @@ def _(preds, labels, hw, strides):
             preds.new_empty((B, A)), preds.new_empty((B,), dtype=torch.int32), preds.new_empty((B,), dtype=torch.int32))
 
 
+# ------------------------------------------------------------------------------------- format_dets
+def format_dets_raw(dets: torch.Tensor, counts: torch.Tensor, inv_scales: torch.Tensor) -> torch.Tensor:
+    """Device part of format_outputs: [B,max_det,6] + counts + per-image (float)(1/scale) -> [B,max_det,8] rows
+    (x1,y1,x2,y2,w,h,score,class), boxes rescaled exactly as `bboxes /= scale` does on CUDA tensors."""
+    d = _check_cuda_f32(dets, "dets")
+    s_ = _check_cuda_f32(inv_scales, "inv_scales")
+    if d.dim() != 3 or d.shape[2] != 6 or counts.dtype != torch.int32 or not counts.is_cuda:
+        raise ValueError("dets must be [B,max_det,6] fp32 and counts [B] int32, both CUDA")
+    B, max_det, _ = d.shape
+    out = torch.empty((B, max_det, 8), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        rc = _lib.lib().plyolo_format_dets_f32(d.data_ptr(), counts.contiguous().data_ptr(), s_.data_ptr(), B, max_det,
+                                               out.data_ptr(), _stream_ptr(d.device))
+    _lib.check(rc, "plyolo_format_dets_f32")
+    return out
+
+
+format_dets = torch.library.custom_op("plyolo::format_dets", format_dets_raw, mutates_args=())
+
+
+@format_dets.register_fake
+def _(dets, counts, inv_scales):
+    return dets.new_empty((dets.shape[0], dets.shape[1], 8))
+
+
 # --------------------------------------------------------------------------------------- bboxes_iou
 def bboxes_iou_raw(bboxes_a: torch.Tensor, bboxes_b: torch.Tensor, xyxy: bool) -> torch.Tensor:
     a = _check_cuda_f32(bboxes_a, "bboxes_a")

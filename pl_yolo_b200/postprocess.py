@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Union
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -59,10 +60,18 @@ def postprocess_dense(predictions: Union[torch.Tensor, LazyPredictions], conf_th
     return ops.postprocess_raw(p, conf_thre, nms_thre, class_agnostic, MAX_NMS, MAX_DET, flavor)
 
 
+class DetList(list):
+    """What `postprocess` returns: the reference's list (one `[n_i, 6]` tensor or None per image) that also
+    remembers the dense batch result, so that `format_outputs` can rescale / convert the whole batch with one
+    kernel and one device->host copy instead of one `.cpu()` per detection."""
+    dense = None   # (dets [B,max_det,6], counts [B] int32) on the device
+    counts_host = None
+
+
 def postprocess(predictions, conf_thre=0.7, nms_thre=0.45, class_agnostic=False) -> List[Optional[torch.Tensor]]:
     """postprocess.py:7 — rows (x1, y1, x2, y2, confidence, class_pred), score-descending."""
     B = predictions.shape[0]
-    output: List[Optional[torch.Tensor]] = [None for _ in range(B)]
+    output = DetList([None for _ in range(B)])
     if B == 0 or predictions.shape[1] == 0:
         return output
     dets, counts, _ = postprocess_dense(predictions, conf_thre, nms_thre, class_agnostic)
@@ -70,7 +79,56 @@ def postprocess(predictions, conf_thre=0.7, nms_thre=0.45, class_agnostic=False)
     for i in range(B):
         if n[i]:
             output[i] = dets[i, : n[i]]
+    output.dense, output.counts_host = (dets, counts), n
     return output
+
+
+def format_outputs(outputs, ids, hws, val_size, class_ids, labels=None):
+    """Drop-in for models/evaluators/postprocess.py:95-138.  Same arguments, same results — `json_list` (COCO
+    dicts, prediction order) and `det_list[image][class]` (VOC arrays of x1,y1,x2,y2,score) — and, like the
+    reference, the boxes of `outputs` end up divided by the image's scale in place.  The per-detection Python
+    loop with a `.cpu()` per box is replaced by one kernel (`bboxes /= scale`, xyxy2xywh) and one copy."""
+    n_img = len(outputs)
+    json_list = []
+    det_list = [[np.empty(shape=[0, 5]) for _ in range(len(class_ids))] for _ in range(n_img)]
+    if n_img == 0:
+        return json_list, det_list
+    dense = getattr(outputs, "dense", None)
+    if dense is None:  # a plain list (e.g. produced elsewhere): pad it to the dense layout first
+        first = next((o for o in outputs if o is not None), None)
+        if first is None:
+            return json_list, det_list
+        max_det = max(o.shape[0] for o in outputs if o is not None)
+        dets = first.new_zeros((n_img, max_det, 6))
+        cnt = [0 if o is None else int(o.shape[0]) for o in outputs]
+        for i, o in enumerate(outputs):
+            if o is not None:
+                dets[i, : cnt[i]] = o
+        counts = torch.tensor(cnt, dtype=torch.int32, device=dets.device)
+    else:
+        (dets, counts), cnt = dense, outputs.counts_host
+    # scale = min(val_size[0] / float(img_w), val_size[1] / float(img_h)) in Python doubles (postprocess.py:111)
+    scales = [min(val_size[0] / float(w), val_size[1] / float(h)) for h, w in zip(hws[0], hws[1])][:n_img]
+    # `tensor /= python_float` on CUDA multiplies by the reciprocal taken in double and rounded to fp32
+    sc = torch.tensor([1.0 / v for v in scales], dtype=torch.float64).to(torch.float32).to(dets.device)
+    rows = ops.format_dets_raw(dets, counts, sc)
+    # the reference's in-place `bboxes /= scale` is visible to the caller through `outputs`
+    for i, o in enumerate(outputs):
+        if o is not None:
+            o[:, 0:4] = rows[i, : cnt[i], 0:4]
+    host = rows.cpu().numpy()  # the one device->host copy
+    for i, img_id in zip(range(n_img), ids):
+        if outputs[i] is None:
+            continue
+        r = host[i, : cnt[i]]
+        cls = r[:, 7].astype(np.int64)
+        xywh = r[:, [0, 1, 4, 5]]
+        for j in range(cnt[i]):
+            json_list.append({"image_id": int(img_id), "category_id": class_ids[int(cls[j])],
+                              "bbox": xywh[j].tolist(), "score": r[j, 6].item(), "segmentation": []})
+        for c in range(len(class_ids)):
+            det_list[i][c] = r[cls == c][:, [0, 1, 2, 3, 6]]
+    return json_list, det_list
 
 
 demo_postprocess = postprocess  # postprocess.py:51-92 is a verbatim copy of :7-48

@@ -5,7 +5,7 @@ import torch
 
 from golden_util import eval_preds_of, heads_of, labels_of, load, names
 from oracle import torch_ops_replay as R
-from pl_yolo_b200 import LazyPredictions, YOLOXDecoder, YOLOXLoss, bboxes_iou, postprocess, synth
+from pl_yolo_b200 import LazyPredictions, YOLOXDecoder, YOLOXLoss, bboxes_iou, ops, postprocess, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -84,3 +84,56 @@ def test_training_step_backward_runs():
 def test_bboxes_iou_guard():
     with pytest.raises(IndexError):
         bboxes_iou(torch.zeros(2, 5, device=DEV), torch.zeros(3, 4, device=DEV))
+
+
+def _ref_format_outputs(outputs, ids, hws, val_size, class_ids):
+    """models/evaluators/postprocess.py:95-138 replayed op for op on the tensors' own device."""
+    json_list = []
+    det_list = [[np.empty(shape=[0, 5]) for _ in range(len(class_ids))] for _ in range(len(outputs))]
+    for i, (output, img_h, img_w, img_id) in enumerate(zip(outputs, hws[0], hws[1], ids)):
+        if output is None:
+            continue
+        bboxes = output[:, 0:4]
+        scale = min(val_size[0] / float(img_w), val_size[1] / float(img_h))
+        bboxes /= scale
+        coco = bboxes.clone()
+        coco[:, 2] = bboxes[:, 2] - bboxes[:, 0]
+        coco[:, 3] = bboxes[:, 3] - bboxes[:, 1]
+        scores, clses = output[:, 4], output[:, 5]
+        for cocobox, score, cls in zip(coco, scores, clses):
+            json_list.append({"image_id": int(img_id), "category_id": class_ids[int(cls)],
+                              "bbox": cocobox.cpu().numpy().tolist(), "score": score.cpu().numpy().item(), "segmentation": []})
+        for c in range(len(class_ids)):
+            det_list[i][c] = output[clses == c, 0:5].cpu().numpy()
+    return json_list, det_list
+
+
+def test_format_outputs_matches_reference_op_chain():
+    """N1: format_outputs — one kernel + one D2H instead of a .cpu() per detection; results and the
+    in-place rescale of `outputs` are bit-identical to the reference's op chain on CUDA tensors."""
+    from pl_yolo_b200 import format_outputs
+    B = 5
+    heads = [cu(h) for h in synth.make_heads(B, 320, 80, 61)]
+    heads[0][3, 4] = -30.0; heads[1][3, 4] = -30.0; heads[2][3, 4] = -30.0  # image 3: nothing passes -> None
+    preds, _ = ops.decode_raw(heads, [8, 16, 32], True)
+    ids = [11, 12, 13, 14, 15]
+    hws = (torch.tensor([480, 333, 1000, 320, 517]), torch.tensor([640, 500, 1777, 320, 389]))
+    class_ids = list(range(1, 81))
+    ours = postprocess(preds, 0.3, 0.65)
+    assert ours[3] is None
+    ref_in = [None if o is None else o.clone() for o in ours]
+    jl, dl = format_outputs(ours, ids, hws, (320, 320), class_ids, None)
+    rj, rd = _ref_format_outputs(ref_in, ids, hws, (320, 320), class_ids)
+    assert jl == rj
+    for a, b in zip(dl, rd):
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and np.array_equal(x, y)
+    for o, r in zip(ours, ref_in):  # the in-place side effect on `outputs`
+        assert (o is None) == (r is None)
+        if o is not None:
+            assert torch.equal(o, r)
+    # a plain list (not produced by our postprocess) takes the padding route
+    plain = [None if o is None else o.clone() for o in ref_in]
+    jl2, _ = format_outputs(plain, ids, hws, (1.0, 1.0), class_ids, None)
+    rj2, _ = _ref_format_outputs([None if o is None else o.clone() for o in ref_in], ids, hws, (1.0, 1.0), class_ids)
+    assert jl2 == rj2
