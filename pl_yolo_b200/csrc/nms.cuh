@@ -25,9 +25,13 @@
 
 #include <cfloat>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace plyolo {
+
+namespace cg = cooperative_groups;
 
 // torchvision's IoU test; a = kept (higher-scored, "row") box, b = later ("column") box.
 // Exactly `inter / union > thr` with torchvision's roundings, but the IEEE division only runs inside a
@@ -100,17 +104,20 @@ __host__ __device__ inline size_t nms_smem_bytes(const int sort_cap, const int f
 }
 
 // nms_group_kernel: the single-CTA layout (fallback), its own fast layout, or the merge's record lists
+// nms_group_kernel: the single-CTA layout (fallback) or its own fast layout followed by the merge's key lists
+__host__ __device__ inline size_t nms_group_merge_offset(const int fast_cap) {
+    return ((size_t)fast_cap * 40 + (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned) + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t nms_group_smem_bytes(const int sort_cap, const int fast_cap, const int max_det, const int NT) {
     size_t m = nms_smem_bytes(sort_cap, fast_cap, max_det, NT);
-    const size_t fast_b = (size_t)fast_cap * 40 + (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned);
-    const size_t merge_b = (size_t)kGroups * max_det * sizeof(KeptRec);
+    const size_t fast_b = nms_group_merge_offset(fast_cap) + ((size_t)kGroups * max_det + 64) * sizeof(unsigned long long);
     if (fast_b > m) m = fast_b;
-    if (merge_b > m) m = merge_b;
     return (m + 15) & ~(size_t)15;
 }
 
 struct NmsParams {
     int B, NT, max_nms, max_det, flavor, agnostic, sort_cap, fast_cap;
+    int merge_ok;  // the dynamic shared memory includes the cluster merge's key lists (kGroups * max_det keys)
     float thr_f;
     double thr_d;
     CandWs ws;
@@ -890,16 +897,16 @@ constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a t
 // The image's last CTA to finish merges the kGroups sorted lists by rank (binary searches) and writes
 // the first max_det rows.  Anything else — and any image where a cross-class pair suppresses — is
 // handled by one CTA with nms_image (exact general algorithm).
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
+__global__ void __cluster_dims__(kGroups, 1, 1) __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ int g_cnt[kMaxClasses], g_begin[kMaxClasses], g_cursor[kMaxClasses], g_order[kMaxClasses];
     __shared__ int g_cum[kMaxClasses + 1];             // first sweep item of the oi-th largest class
     __shared__ volatile int g_fin[kMaxClasses];        // chunks of the class that are final
     __shared__ volatile int g_kcum[kFastCap / 32 + kMaxClasses];  // per sweep item: keeps of its class up to and including it
     __shared__ int g_wbase[kFastCap / 32 + 1];
-    __shared__ int g_next, g_next2, g_fallback, g_last, g_nbig;
+    __shared__ int g_next, g_next2, g_fallback, g_nbig;
     __shared__ unsigned x_minx[kMaxClasses], x_miny[kMaxClasses];  // per class: min x1 / y1 of its cross boxes (ordered uint)
-    __shared__ int g_lcount[kGroups + 1];
+    __shared__ int c_kpub, c_fallback;               // read by the other CTAs of the cluster
     __shared__ float4 x_box[kMaxCross];              // cross boxes, class offset applied
     __shared__ unsigned long long x_key[kMaxCross];
     const int g = blockIdx.x, b = blockIdx.y;
@@ -923,7 +930,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
     const bool per_class = !p.agnostic && 4 * (long long)total > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
     const bool use_off = !p.agnostic && !per_class;
     const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
-    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && p.max_det <= kRecCap &&
+    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && p.merge_ok &&
                       (!use_off || (filter_ok && xc <= kMaxCross));
     if (!fast) {
         if (g == 0) {
@@ -1159,9 +1166,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
     }
     if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 3), (unsigned long long)clock64());
     __syncthreads();
-    if (tid == 0 && g_fallback) atomicOr(&ctr[kGroups + 3], 1);
 
-    // ---- kept keys of the group: class stripped, compacted, sorted; the first max_det published as records
+    // ---- kept keys of the group: class stripped, compacted (sorted and cut to max_det only if there are more)
     unsigned long long *keys2 = reinterpret_cast<unsigned long long *>(box_s);
     const int nwords = (n + 31) >> 5;
     if (warp == 0) {
@@ -1190,89 +1196,97 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsPara
         if ((wbits >> (i & 31)) & 1u)
             keys2[g_wbase[i >> 5] + __popc(wbits & ((1u << (i & 31)) - 1u))] = keys[i] & kOrderMask;
     }
-    int n2 = 64;
-    while (n2 < Kg) n2 <<= 1;
-    for (int i = Kg + tid; i < n2; i += kNmsThreads) keys2[i] = ~0ull;
-    __syncthreads();
-    GPROF(4);
-    block_sort(keys2, n2);
-    GPROF(5);
-    const int Kpub = min(Kg, p.max_det);
-    KeptRec *pub = p.ws.krec + ((size_t)b * kGroups + g) * kRecCap;
-    for (int i = tid; i < Kpub; i += kNmsThreads) {
-        const unsigned long long key = keys2[i];
-        const int slot = key_slot(key);
-        KeptRec r;
-        r.key = key;
-        r.score = p.ws.score[slot0 + slot];
-        r.meta = p.ws.meta[slot0 + slot];
-        r.box = p.ws.box[slot0 + slot];
-        pub[i] = r;
+    if (Kg > p.max_det) {  // rare: only the group's first max_det keeps in global order can reach the output
+        int n2 = 64;
+        while (n2 < Kg) n2 <<= 1;
+        for (int i = Kg + tid; i < n2; i += kNmsThreads) keys2[i] = ~0ull;
+        __syncthreads();
+        block_sort(keys2, n2);
     }
-    if (tid == 0) p.ws.kcount[b * kGroups + g] = Kpub;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) g_last = (atomicAdd(&ctr[kGroups + 2], 1) == kGroups - 1) ? 1 : 0;
-    __syncthreads();
-    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = xc; prof[13] = g_last; }
+    const int Kpub = min(Kg, p.max_det);
+    if (tid == 0) { c_kpub = Kpub; c_fallback = g_fallback; }
+    GPROF(4);
+    // ---- merge across the image's kGroups CTAs (one thread-block cluster) through distributed shared memory:
+    // every CTA copies the other groups' kept keys, ranks its own keys among all of them by counting (keys
+    // are distinct: rank = number of smaller keys = row of the output) and writes its own rows.
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    GPROF(5);
+    unsigned long long *allk = reinterpret_cast<unsigned long long *>(nms_smem + nms_group_merge_offset(p.fast_cap));
+    int kq[kGroups], total_k = 0, fb = 0;
+#pragma unroll
+    for (int q = 0; q < kGroups; ++q) {
+        kq[q] = *cluster.map_shared_rank(&c_kpub, q);
+        fb |= *cluster.map_shared_rank(&c_fallback, q);
+        total_k += kq[q];
+    }
+    {
+        int base = 0;
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) {
+            const unsigned long long *src = cluster.map_shared_rank(keys2, q);
+            for (int i = tid; i < kq[q]; i += kNmsThreads) allk[base + i] = src[i];
+            base += kq[q];
+        }
+        for (int i = total_k + tid; i < ((total_k + 63) & ~63); i += kNmsThreads) allk[i] = ~0ull;
+    }
+    cluster.sync();  // nobody reads another CTA's shared memory past this point (also a CTA barrier)
     GPROF(6);
-    if (!g_last) return;
-    __threadfence();
-    if (__ldcg(&ctr[kGroups + 3])) {
+    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = xc; prof[13] = 1; }
+    if (fb) {
         // a pair of different classes suppresses: the exact global sweep redoes the image
-        NmsParams q = p;
-        q.prof = nullptr;
-        nms_image(q, b, nms_smem);
+        if (g == 0) {
+            NmsParams q = p;
+            q.prof = nullptr;
+            nms_image(q, b, nms_smem);
+            if (prof && tid == 0) prof[14] = 1;
+        }
         GPROF(7);
-        if (prof && tid == 0) prof[14] = 1;
         return;
     }
-    // ---- merge: every list is read blind (up to max_det records each) together with the counts; the rank
-    // of a kept key = its position in its own list + the number of smaller keys in the other lists
-    KeptRec *recs = reinterpret_cast<KeptRec *>(nms_smem);  // [kGroups][max_det]
-    if (tid < kGroups) g_lcount[tid] = __ldcg(&p.ws.kcount[b * kGroups + tid]);
-    for (int e = tid; e < kGroups * p.max_det; e += kNmsThreads) {
-        const int q = e / p.max_det, i = e - q * p.max_det;
-        const float4 *src = reinterpret_cast<const float4 *>(p.ws.krec + ((size_t)b * kGroups + q) * kRecCap + i);
-        float4 *dst = reinterpret_cast<float4 *>(recs + e);
-        dst[0] = __ldcg(src);
-        dst[1] = __ldcg(src + 1);
-    }
-    __syncthreads();
-    int Kt = 0;
+    const int nkept = min(total_k, p.max_det);
+    // rank of every own key = number of smaller keys in all lists (padded with +inf to a multiple of 64):
+    // 8 threads per key, 8 independent compares per trip; the key's record is fetched while the count runs
+    constexpr int kSubT = 8;
+    const int total_pad = (total_k + 63) & ~63;
+    for (int i0 = 0; i0 < Kpub; i0 += kNmsThreads / kSubT) {
+        const int i = i0 + tid / kSubT, sub = tid % kSubT;
+        const bool owner = i < Kpub && sub == 0;
+        const unsigned long long key = i < Kpub ? keys2[i] : 0ull;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        int meta = 0;
+        float sc = 0.f;
+        if (owner) {
+            const int slot = key_slot(key);
+            bx = p.ws.box[slot0 + slot];
+            meta = p.ws.meta[slot0 + slot];
+            sc = p.ws.score[slot0 + slot];
+        }
+        int rank = 0;
+        if (i < Kpub) {
+            for (int j = sub; j < total_pad; j += 8 * kSubT) {
 #pragma unroll
-    for (int q = 0; q < kGroups; ++q) Kt += g_lcount[q];
-    const int nkept = min(Kt, p.max_det);
-    for (int e = tid; e < kGroups * p.max_det; e += kNmsThreads) {
-        const int q = e / p.max_det, i = e - q * p.max_det;
-        if (i >= g_lcount[q]) continue;
-        const KeptRec r = recs[e];
-        int rank = i;
-#pragma unroll
-        for (int u = 0; u < kGroups; ++u) {
-            if (u == q) continue;
-            int lo = 0, hi = g_lcount[u];  // first position with key' > key (keys are distinct)
-            const KeptRec *lst = recs + u * p.max_det;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (lst[mid].key < r.key) lo = mid + 1; else hi = mid;
+                for (int u = 0; u < 8; ++u) rank += allk[j + u * kSubT] < key ? 1 : 0;
             }
-            rank += lo;
         }
-        if (rank < nkept) {
+#pragma unroll
+        for (int o = 1; o < kSubT; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (owner && rank < nkept) {
             float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + rank) * 6);
-            d[0] = make_float2(r.box.x, r.box.y);
-            d[1] = make_float2(r.box.z, r.box.w);
-            d[2] = make_float2(r.score, (float)(r.meta >> 24));
-            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = r.meta & 0xffffff;
+            d[0] = make_float2(bx.x, bx.y);
+            d[1] = make_float2(bx.z, bx.w);
+            d[2] = make_float2(sc, (float)(meta >> 24));
+            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = meta & 0xffffff;
         }
     }
-    for (int i = nkept + tid; i < p.max_det; i += kNmsThreads) {
-        float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
-        d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
-        if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
+    if (g == 0) {
+        for (int i = nkept + tid; i < p.max_det; i += kNmsThreads) {
+            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
+            d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
+            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
+        }
+        if (tid == 0) p.counts[b] = nkept;
     }
-    if (tid == 0) p.counts[b] = nkept;
     GPROF(7);
 #undef GPROF
 }

@@ -31,6 +31,7 @@ constexpr int kMaxCross = 512;  // boxes that may reach into another class's off
 constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
 constexpr int kImgCtr = 8;      // ints per image in the counter block (zeroed before every call)
 
+constexpr size_t kNmsSmemLimit = 190 * 1024;  // dynamic shared memory of the NMS kernels (33 KB are static)
 constexpr int kRecCap = 1024;   // >= max_det: a group contributes at most max_det rows to the image's output
 
 struct __align__(16) KeptRec {  // one kept box as the merge needs it
@@ -102,6 +103,13 @@ __device__ __forceinline__ void group_barrier(const int bar_id) {
     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
+// three-input maximum (FMNMX3, sm_100+); NaN operands are ignored like fmaxf
+__device__ __forceinline__ float max3f(const float a, const float b, const float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // Scores one staged tile (128 threads, `tid` in [0,128), barrier `bar_id`).  `tile` is read-only here; after
 // the call returns the group no longer needs it IF `release` was invoked (it is called once, by every thread,
 // right after the last read of the tile).
@@ -138,50 +146,62 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         if (tid < cnt) {
             const float so = sigmoid_ref(tile[4 * kPpTile + tid]);  // yolox_loss.py:26
             if (so >= p.conf_thr) {
-                // one branch-free sweep, 4 independent chains (classes = chain mod 4: the loads and the dependent
-                // min/max of different chains overlap; 8 chains measured slower): largest and second largest raw
-                // logit and the first index of the largest
-                constexpr int NCH = 4;
+                // Stage 1 (every thread that can still pass): the largest raw logit of every chunk of 16 classes
+                // with three-input max (FMNMX3): 1.5 instructions per class.  Stage 2 (only the anchors that
+                // survive the pre-filter, i.e. real candidates): the chunks whose maximum reaches the window are
+                // rescanned in ascending class order for the first arg max over the sigmoid VALUES.
+                constexpr int CS = 16, NCK = (PLYOLO_MAX_CLASSES + CS - 1) / CS;
                 const float *col = tile + 5 * kPpTile + tid;
-                float m1[NCH], m2[NCH];
-                int i1[NCH];
+                float M[NCK];
 #pragma unroll
-                for (int u = 0; u < NCH; ++u) { m1[u] = -3.0e38f; m2[u] = -3.0e38f; i1[u] = 0; }
-                int c = 0;
-                for (; c + NCH - 1 < p.C; c += NCH) {
-                    float x[NCH];
+                for (int k = 0; k < NCK; ++k) {
+                    M[k] = -3.0e38f;
+                    if (k * CS < p.C) {
+                        const float *ck = col + k * CS * kPpTile;
+                        if ((k + 1) * CS <= p.C) {
+                            float x[CS];
 #pragma unroll
-                    for (int u = 0; u < NCH; ++u) x[u] = col[(c + u) * kPpTile];
-#pragma unroll
-                    for (int u = 0; u < NCH; ++u) {
-                        m2[u] = fmaxf(m2[u], fminf(x[u], m1[u]));
-                        i1[u] = x[u] > m1[u] ? c + u : i1[u];
-                        m1[u] = fmaxf(m1[u], x[u]);
+                            for (int u = 0; u < CS; ++u) x[u] = ck[u * kPpTile];
+                            const float q0 = max3f(x[0], x[1], x[2]), q1 = max3f(x[3], x[4], x[5]);
+                            const float q2 = max3f(x[6], x[7], x[8]), q3 = max3f(x[9], x[10], x[11]);
+                            const float q4 = max3f(x[12], x[13], x[14]);
+                            M[k] = max3f(max3f(q0, q1, q2), max3f(q3, q4, x[15]), -3.0e38f);
+                        } else {
+                            for (int cc = k * CS; cc < p.C; ++cc) M[k] = fmaxf(M[k], ck[(cc - k * CS) * kPpTile]);
+                        }
                     }
                 }
-                for (; c < p.C; ++c) {
-                    const float x = col[c * kPpTile];
-                    m2[0] = fmaxf(m2[0], fminf(x, m1[0]));
-                    i1[0] = x > m1[0] ? c : i1[0];
-                    m1[0] = fmaxf(m1[0], x);
-                }
+                float m = M[0];
 #pragma unroll
-                for (int u = 1; u < NCH; ++u) {  // fold chain u into chain 0
-                    m2[0] = fmaxf(fmaxf(m2[0], m2[u]), fminf(m1[0], m1[u]));
-                    i1[0] = m1[u] > m1[0] ? i1[u] : (m1[u] == m1[0] ? min(i1[0], i1[u]) : i1[0]);
-                    m1[0] = fmaxf(m1[0], m1[u]);
-                }
-                const float m = m1[0];
+                for (int k = 1; k < NCK; ++k) m = fmaxf(m, M[k]);
                 const float sm = sigmoid_ref(m);  // yolox_loss.py:27
                 if ((so * sm) * 1.00001f >= p.conf_thr) {
                     const float em = expf(-m);
                     float t = -logf(em + 2.0e-6f * (1.0f + em));
                     t = t - 1.0e-5f * (1.0f + fabsf(t));
                     if (!(t <= m)) t = m;  // NaN / overflow guard: at least the max itself is evaluated
+                    // Normally only the arg max lies inside the window: ONE chunk reaches t and one logit of it.
+                    // That chunk is rescanned branch-free (every lane its own chunk); anything else (saturation,
+                    // near ties) takes the exact sweep over the sigmoid values.
+                    int kstar = 0, nhit = 0;
+#pragma unroll
+                    for (int k = NCK - 1; k >= 0; --k) {
+                        const bool h = k * CS < p.C && M[k] >= t;
+                        kstar = h ? k : kstar;
+                        nhit += h ? 1 : 0;
+                    }
+                    const float *ck = col + kstar * CS * kPpTile;
+                    unsigned hits = 0u;
+#pragma unroll
+                    for (int u = 0; u < CS; ++u) {
+                        const float x = (kstar * CS + u < p.C) ? ck[u * kPpTile] : -3.0e38f;
+                        hits |= (x >= t) ? (1u << u) : 0u;
+                    }
                     float best = sm;
-                    cls = i1[0];
-                    if (m2[0] >= t) {  // rare: several logits inside the window (saturation, near ties): exact sweep
+                    cls = kstar * CS + __ffs(hits) - 1;
+                    if (nhit != 1 || __popc(hits) != 1) {  // rare: several logits inside the window
                         best = -1.f;
+                        cls = 0;
                         for (int cc = 0; cc < p.C; ++cc) {
                             const float x = col[cc * kPpTile];
                             if (x >= t) {
@@ -336,11 +356,19 @@ struct TmapPack {
     CUtensorMap m[PLYOLO_MAX_LEVELS];
 };
 
-__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, const int c0, const int c1, uint64_t *bar) {
+// The head maps are read exactly once: an evict-first L2 policy keeps the 91 MB stream from pushing the
+// candidate records (written by this kernel, read back by the NMS kernel a few microseconds later) out to DRAM.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, const int c0, const int c1, uint64_t *bar,
+                                            const uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
             smem_u32(dst_smem)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 
@@ -364,6 +392,7 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
     if (warp < kProducers) {
         // ---- producers
         if ((!FUSED || use_tmap) && warp > 0) return;  // one request per tile: one warp is plenty
+        const uint64_t policy = l2_evict_first_policy();
         for (int seq = 0;; ++seq) {
             const int t = tile_of(seq);
             if (t >= total) break;
@@ -374,7 +403,7 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
             if (FUSED && use_tmap) {
                 if (lane == 0) {
                     mbar_expect_tx(&full_bar[s], (uint32_t)(p.ch * kPpTile * 4));  // the whole box, zero fill included
-                    tma_load_2d(dst, &tmaps.m[tc.l], tc.a0, tc.b * p.ch, &full_bar[s]);
+                    tma_load_2d(dst, &tmaps.m[tc.l], tc.a0, tc.b * p.ch, &full_bar[s], policy);
                 }
                 continue;
             }
@@ -474,8 +503,13 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     np.fast_cap = cap < kFastCap ? cap : kFastCap;
     np.ws = ws; np.dets = dets; np.counts = counts; np.keep_idx = keep_idx;
     np.prof = g_nms_prof;
-    const size_t smem = nms_group_smem_bytes(cap, np.fast_cap, max_det, NT);
-    PLYOLO_REQUIRE(smem <= 190 * 1024, "nms working set (%zu B) exceeds shared memory", smem);
+    size_t smem = nms_group_smem_bytes(cap, np.fast_cap, max_det, NT);
+    np.merge_ok = 1;
+    if (smem > kNmsSmemLimit) {  // very large max_det: no room for the merge lists, the images take the single-CTA path
+        smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
+        np.merge_ok = 0;
+    }
+    PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
     cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     record_stage_event(1, stream);
     nms_group_kernel<<<dim3(kGroups, B), kNmsThreads, smem, stream>>>(np);

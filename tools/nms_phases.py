@@ -17,7 +17,7 @@ ops.decode_postprocess_raw(heads, [8, 16, 32], 0.01, 0.65, False, 10000, 300, 0)
 torch.cuda.synchronize()
 L.plyolo_debug_nms_profile(None)
 p = prof.cpu().numpy().astype(np.int64)
-names = ["stage+hist", "prefix+scatter", "sort+gather", "sweep", "compact", "sort", "publish", "merge/fallback"]
+names = ["stage+hist", "prefix+scatter", "sort+gather", "sweep", "compact", "cluster sync", "gather lists", "rank+write"]
 t = np.stack([p[:, 0], p[:, 1], p[:, 2], p[:, 8], p[:, 3], p[:, 4], p[:, 5], p[:, 6], p[:, 7]], 1)
 us = lambda a: a / 1965.0
 d = np.diff(t[:, :8], axis=1)
@@ -25,7 +25,7 @@ print("phase us over (image, group) CTAs: mean / max")
 for i, n in enumerate(names[:7]):
     print("  %-15s %7.2f %7.2f" % (n, us(d[:, i]).mean(), us(d[:, i]).max()))
 last = p[:, 13] == 1
-print("  %-15s %7.2f %7.2f  (last CTA of each image)" % (names[7], us(t[last, 8] - t[last, 7]).mean(), us(t[last, 8] - t[last, 7]).max()))
+print("  %-15s %7.2f %7.2f" % (names[7], us(t[last, 8] - t[last, 7]).mean(), us(t[last, 8] - t[last, 7]).max()))
 print("  CTA total (to publish)  %7.2f %7.2f" % (us(t[:, 7] - t[:, 0]).mean(), us(t[:, 7] - t[:, 0]).max()))
 print("  last CTA total          %7.2f %7.2f" % (us(t[last, 8] - t[last, 0]).mean(), us(t[last, 8] - t[last, 0]).max()))
 print("n per group", p[:, 10].reshape(B, G).tolist())
