@@ -35,9 +35,10 @@ constexpr int kPrepSplit = 4;     // CTAs per image in the prep kernel
 constexpr int kGtPerCta = 8;      // GTs per CTA in the match kernel
 constexpr int kMatchWarps = 16;   // two per GT during the IoU sweep
 constexpr int kMatchThreads = kMatchWarps * 32;
-constexpr int kSweepSplit = 8;   // CTAs per image in the IoU sweep: each takes one slice of the candidates
-constexpr int kSweepThreads = 256;
-constexpr int kSweepGtSplit = 4;  // ... and one quarter of the image's GTs (grid.x = kSweepSplit * kSweepGtSplit)
+constexpr int kSweepSub = 4;      // IoU sweep: warps per GT (each takes every 4th candidate group the GT overlaps)
+constexpr int kSweepGts = 2;      // GTs of one image per CTA
+constexpr int kSweepThreads = kSweepGts * kSweepSub * 32;
+constexpr int kSweepChunk = 1024;  // candidate groups listed per pass (all of them at 640^2)
 constexpr int kMaxBoth = 36 * PLYOLO_MAX_LEVELS;  // 5x5 centre cells per level (6x6 if an edge rounds outward)
 constexpr int kExtraEval = 4;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
 constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
@@ -63,7 +64,9 @@ struct SimParams {
     int *res_g;           // [B,A]  conflict resolution: argmin GT ...
     float *res_iou;       // [B,A]  ... and its IoU
     short *rect;          // [B,Lmax,n_levels,8] in-box x0,x1,y0,y1 | in-centre x0,x1,y0,y1 (inclusive)
-    float *top_part;      // [B,Lmax,kSweepSplit,10] the 10 largest IoUs of every GT inside every candidate slice
+    float4 *grp_box;      // [B,A/32+1] union box of every group of 32 consecutive candidates
+    int *dyn_k;           // [B,Lmax] dynamic k of every GT (:336-340)
+    int force_exact;      // debug: the IoU sweep takes its exact warp-wide list for every GT
     long long *prof;      // debug: [B][gridDim.x][16] phase timestamps of the match kernel, or null
 };
 
@@ -205,7 +208,7 @@ __device__ __forceinline__ void set_bits(unsigned *bitmap, const int p0, const i
 }
 
 __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimParams p) {
-    extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1]
+    extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1] | this CTA's candidates [A/4 + 128]
     __shared__ int s_G, s_warp[kPrepThreads / 32];
     const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (p.A + 31) >> 5;
@@ -283,39 +286,74 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
         __syncthreads();
     }
     const int Nc = run;
-    // this CTA's quarter of the words: candidate list, then the gather of the candidates' boxes
-    const int w_per = (nwords + kPrepSplit - 1) / kPrepSplit;
-    const int w_lo = min(q * w_per, nwords), w_hi = min(w_lo + w_per, nwords);
-    int *ca = p.cand_anchor + (size_t)b * p.A;
-    for (int w = w_lo + tid; w < w_hi; w += kPrepThreads) {
-        unsigned m = bm_fg[w];
-        if (w == nwords - 1 && (p.A & 31)) m &= (1u << (p.A & 31)) - 1u;
-        int n = word_base[w];
-        while (m) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            ca[n++] = (w << 5) + bit;
-        }
-    }
-    __syncthreads();  // this CTA's part of the candidate list (global) is complete
-    const int n_lo = w_lo < nwords ? word_base[w_lo] : Nc, n_hi = w_hi < nwords ? word_base[w_hi] : Nc;
+    // This CTA's share of the candidates: whole groups of 32 consecutive candidates.  The words holding them are
+    // expanded into the candidate list (global, for the match kernel) and a shared copy for the gather below,
+    // so no CTA depends on another CTA's part of the list.
     float4 *cb = p.cand_box + (size_t)b * p.A;
     float *car = p.cand_area + (size_t)b * p.A;
-    for (int n0 = n_lo + tid; n0 < n_hi; n0 += 4 * kPrepThreads) {
-        float4 pb[4];
+    float4 *gb = p.grp_box + (size_t)b * (p.A / 32 + 1);
+    int *ca = p.cand_anchor + (size_t)b * p.A;
+    int *my_list = word_base + nwords + 1;  // [n1 - n0]
+    const int ngrp = (Nc + 31) >> 5;
+    const int gp = (ngrp + kPrepSplit - 1) / kPrepSplit;
+    const int gq_lo = min(q * gp, ngrp), gq_hi = min(gq_lo + gp, ngrp);
+    const int n0 = gq_lo * 32, n1 = min(gq_hi * 32, Nc);
+    auto word_of = [&](const int n) {
+        int lo = 0, hi = nwords;  // word_base[lo] <= n < word_base[hi]  (word_base[nwords] == Nc)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (word_base[mid] <= n) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+    if (n0 < n1) {
+        const int w_first = word_of(n0), w_last = word_of(n1 - 1);
+        for (int w = w_first + tid; w <= w_last; w += kPrepThreads) {
+            unsigned m = bm_fg[w];
+            if (w == nwords - 1 && (p.A & 31)) m &= (1u << (p.A & 31)) - 1u;
+            int n = word_base[w];
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                if (n >= n0 && n < n1) {
+                    my_list[n - n0] = (w << 5) + bit;
+                    ca[n] = (w << 5) + bit;
+                }
+                ++n;
+            }
+        }
+    }
+    __syncthreads();
+    // gather of the candidates' boxes (16 of the 340 bytes of each prediction row), one warp per group, two groups
+    // in flight; the group's union box lets the IoU sweep skip groups a GT cannot overlap
+    for (int gq0 = gq_lo + 2 * warp; gq0 < gq_hi; gq0 += 2 * (kPrepThreads / 32)) {
+        float4 pb[2];
+        bool ok[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {  // 4 independent row gathers in flight per thread
-            const int n = n0 + u * kPrepThreads;
-            if (n < n_hi) pb[u] = load_box(p.preds + ((size_t)b * p.A + ca[n]) * p.ch);
+        for (int u = 0; u < 2; ++u) {
+            const int n = (gq0 + u) * 32 + lane;
+            ok[u] = gq0 + u < gq_hi && n < Nc;
+            if (ok[u]) pb[u] = load_box(p.preds + ((size_t)b * p.A + my_list[n - n0]) * p.ch);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int n = n0 + u * kPrepThreads;
-            if (n < n_hi) {
+        for (int u = 0; u < 2; ++u) {
+            if (gq0 + u >= gq_hi) break;  // warp-uniform
+            const int n = (gq0 + u) * 32 + lane;
+            float4 c = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+            if (ok[u]) {
                 // the candidate-side operands of bboxes_iou(xyxy=False) (iou_loss.py:400-410)
-                cb[n] = make_float4(pb[u].x - pb[u].z / 2, pb[u].y - pb[u].w / 2, pb[u].x + pb[u].z / 2, pb[u].y + pb[u].w / 2);
+                c = make_float4(pb[u].x - pb[u].z / 2, pb[u].y - pb[u].w / 2, pb[u].x + pb[u].z / 2, pb[u].y + pb[u].w / 2);
+                cb[n] = c;
                 car[n] = pb[u].z * pb[u].w;
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c.x = fminf(c.x, __shfl_xor_sync(0xffffffffu, c.x, o));
+                c.y = fminf(c.y, __shfl_xor_sync(0xffffffffu, c.y, o));
+                c.z = fmaxf(c.z, __shfl_xor_sync(0xffffffffu, c.z, o));
+                c.w = fmaxf(c.w, __shfl_xor_sync(0xffffffffu, c.w, o));
+            }
+            if (lane == 0) gb[gq0 + u] = c;
         }
     }
     if (q == 0 && tid == 0) {
@@ -449,81 +487,53 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
 }
 
 // ---- K2a: IoU sweep ---------------------------------------------------------------------------
-// Grid (kSweepSplit, B).  The CTA stages ONE slice of the image's candidates (corner boxes, areas, the union
-// box of every group of 32 consecutive candidates) and its warps walk the image's GTs: a GT only visits the
-// groups whose union box it overlaps (the others have IoU 0 throughout) and keeps the 10 largest IoUs of the
-// slice in a warp-resident list (values only, :336-340; bboxes_iou with xyxy=False, iou_loss.py:400-414, the
-// division runs only when a pair can enter the list).  The match kernel merges the kSweepSplit lists.
-__global__ void __launch_bounds__(kSweepThreads) simota_sweep_kernel(const SimParams p, const int slice_cap) {
-    extern __shared__ __align__(16) unsigned char sweep_smem[];
-    float4 *cbox = reinterpret_cast<float4 *>(sweep_smem);             // [slice_cap]
-    float4 *gbox = cbox + slice_cap;                                   // [slice_cap / 32]
-    float *carea = reinterpret_cast<float *>(gbox + slice_cap / 32);   // [slice_cap]
-    const int c = blockIdx.x % kSweepSplit, gq4 = blockIdx.x / kSweepSplit, b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
-    if (G == 0 || Nc == 0) return;
-    const int g_per = (G + kSweepGtSplit - 1) / kSweepGtSplit;
-    const int g_lo = gq4 * g_per, g_hi = min(G, g_lo + g_per);
-    if (g_lo >= g_hi) return;
-    __shared__ int s_next_gt;
-    if (tid == 0) s_next_gt = g_lo;
-    const int per = (((Nc + kSweepSplit - 1) / kSweepSplit) + 31) & ~31;  // slice length, whole groups
-    const int n0 = c * per, cn = max(0, min(per, Nc - n0));
-    const float4 *cb = p.cand_box + (size_t)b * p.A + n0;
-    const float *car = p.cand_area + (size_t)b * p.A + n0;
-    for (int i = tid; i < cn; i += kSweepThreads) {
-        cbox[i] = cb[i];
-        carea[i] = car[i];
-    }
-    __syncthreads();
-    const int ngroups = (cn + 31) >> 5;
-    for (int gq = warp; gq < ngroups; gq += kSweepThreads / 32) {
-        const int n = gq * 32 + lane;
-        float4 u = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
-        if (n < cn) u = cbox[n];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            u.x = fminf(u.x, __shfl_xor_sync(0xffffffffu, u.x, o));
-            u.y = fminf(u.y, __shfl_xor_sync(0xffffffffu, u.y, o));
-            u.z = fmaxf(u.z, __shfl_xor_sync(0xffffffffu, u.z, o));
-            u.w = fmaxf(u.w, __shfl_xor_sync(0xffffffffu, u.w, o));
+// kSweepSub warps per GT (kSweepGts GTs of one image per CTA).  Every warp tests the union boxes of the image's
+// candidate groups 32 at a time and visits its share of the groups the GT overlaps (all other pairs have
+// IoU 0; bboxes_iou with xyxy=False, iou_loss.py:400-414).  Every lane keeps the 4 largest IoUs of ITS
+// candidates (branch-free insertion, no shuffles in the loop; the division only runs when a pair can enter
+// the lane's list); the 10 largest of the image (:336-340, values only) are then extracted from the lane lists.
+// That is exact unless a lane that saw more than 4 overlapping candidates still holds 4 values above the
+// 10th largest — then (rare) the GT is redone with the exact warp-wide list.  dynamic k = clamp(int(sum of the
+// top min(10, Nc)), 1) with ATen's reduce tree goes straight to the match kernel.
+// Exact warp-wide list of the largest IoUs above `floor_v` (lane i = i-th largest; the list starts filled with
+// floor_v, so fewer than 10 larger values leave copies of floor_v behind them).  floor_v = 0 is the plain top-10.
+__device__ __noinline__ float sweep_exact(const float4 *cb, const float *car, const float4 *gb, const int Nc,
+                                          const float g_x1, const float g_y1, const float g_x2, const float g_y2,
+                                          const float area_a, const float floor_v) {
+    const int lane = threadIdx.x & 31;
+    const int ngrp = (Nc + 31) >> 5;
+    // a pair that does not overlap has IoU (+/-)0 and can never displace anything
+    float top = floor_v, thresh = floor_v;
+    for (int q0 = 0; q0 < ngrp; q0 += 32) {
+        bool h = false;
+        if (q0 + lane < ngrp) {
+            const float4 u = __ldg(gb + q0 + lane);
+            h = fmaxf(g_x1, u.x) < fminf(g_x2, u.z) && fmaxf(g_y1, u.y) < fminf(g_y2, u.w);
         }
-        if (lane == 0) gbox[gq] = u;
-    }
-    __syncthreads();
-    for (;;) {  // the warps take the CTA's GTs dynamically: the work per GT varies with its overlaps
-        int g = 0;
-        if (lane == 0) g = atomicAdd(&s_next_gt, 1);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= g_hi) break;
-        const float *L = p.labels + ((size_t)b * p.Lmax + g) * 5;
-        const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
-        const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
-        const float area_a = gw * gh;
-        // lists start at +0: a pair that does not overlap has IoU (+/-)0 and can never displace anything
-        float top = 0.f, thresh = 0.f;
-        for (int q0 = 0; q0 < ngroups; q0 += 32) {
-            bool h = false;
-            if (q0 + lane < ngroups) {
-                const float4 u = gbox[q0 + lane];
-                h = fmaxf(g_x1, u.x) < fminf(g_x2, u.z) && fmaxf(g_y1, u.y) < fminf(g_y2, u.w);
+        unsigned hit = __ballot_sync(0xffffffffu, h);
+        while (hit) {  // eight groups per trip: their loads are in flight together
+            constexpr int U = 8;
+            bool ok[U];
+            float4 cc[U];
+            float ar[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int n = (q0 + (hit ? __ffs(hit) - 1 : 0)) * 32 + lane;
+                ok[u] = hit != 0u && n < Nc;
+                hit &= hit - 1;  // 0 stays 0
+                cc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ar[u] = 0.f;
+                if (ok[u]) { cc[u] = __ldg(cb + n); ar[u] = __ldg(car + n); }
             }
-            unsigned hit = __ballot_sync(0xffffffffu, h);
-            while (hit) {
-                const int gq = q0 + __ffs(hit) - 1;
-                hit &= hit - 1;
-                const int n = gq * 32 + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
                 float v = 0.f;
-                if (n < cn) {
-                    const float4 cc = cbox[n];
-                    const float tlx = fmaxf(g_x1, cc.x), tly = fmaxf(g_y1, cc.y);
-                    const float brx = fminf(g_x2, cc.z), bry = fminf(g_y2, cc.w);
-                    if (tlx < brx && tly < bry) {  // en == 1
-                        const float area_i = (brx - tlx) * (bry - tly);
-                        const float den = (area_a + carea[n]) - area_i;
-                        if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
-                    }
+                const float tlx = fmaxf(g_x1, cc[u].x), tly = fmaxf(g_y1, cc[u].y);
+                const float brx = fminf(g_x2, cc[u].z), bry = fminf(g_y2, cc[u].w);
+                if (ok[u] && tlx < brx && tly < bry) {  // en == 1
+                    const float area_i = (brx - tlx) * (bry - tly);
+                    const float den = (area_a + ar[u]) - area_i;
+                    if (area_i >= (thresh * den) * 0.999f) v = area_i / den;
                 }
                 unsigned m = __ballot_sync(0xffffffffu, v > thresh);
                 if (m) {
@@ -536,8 +546,156 @@ __global__ void __launch_bounds__(kSweepThreads) simota_sweep_kernel(const SimPa
                 }
             }
         }
-        if (lane < 10) p.top_part[(((size_t)b * p.Lmax + g) * kSweepSplit + c) * 10 + lane] = top;
     }
+    return top;
+}
+
+// barrier of the kSweepSub warps that share GT `gl` of the CTA
+__device__ __forceinline__ void gt_barrier(const int gl) {
+    static_assert(kSweepGts == 2, "one named barrier per GT of the CTA");
+    if (gl == 0) asm volatile("bar.sync 1, %0;" ::"n"(kSweepSub * 32) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(kSweepSub * 32) : "memory");
+}
+
+// branch-free insertion of a (a >= 0, or 0 for "nothing") into the descending list t[0] >= ... >= t[kLaneTop-1]
+constexpr int kLaneTop = 6;  // values kept per lane
+__device__ __forceinline__ void lane_insert(float (&t)[kLaneTop], float a) {
+#pragma unroll
+    for (int i = 0; i < kLaneTop - 1; ++i) {
+        const float hi = fmaxf(t[i], a);
+        a = fminf(t[i], a);
+        t[i] = hi;
+    }
+    t[kLaneTop - 1] = fmaxf(t[kLaneTop - 1], a);
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 4) simota_sweep_kernel(const SimParams p) {
+    __shared__ float s_list[kSweepGts][kSweepSub - 1][kLaneTop][32];
+    __shared__ int s_seen[kSweepGts][kSweepSub - 1][32];
+    __shared__ unsigned short s_hit[kSweepGts][kSweepChunk];
+    __shared__ int s_nhit[kSweepGts];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = warp / kSweepSub, ws = warp % kSweepSub;  // GT of the CTA, part of the GT's hit groups
+    const int g = blockIdx.x * kSweepGts + gl;
+    const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
+    if (g >= G || Nc == 0) return;  // uniform for the kSweepSub warps of a GT
+    const float *L = p.labels + ((size_t)b * p.Lmax + g) * 5;
+    const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
+    const float g_x1 = gx - gw / 2, g_y1 = gy - gh / 2, g_x2 = gx + gw / 2, g_y2 = gy + gh / 2;
+    const float area_a = gw * gh;
+    const float4 *cb = p.cand_box + (size_t)b * p.A;
+    const float *car = p.cand_area + (size_t)b * p.A;
+    const float4 *gb = p.grp_box + (size_t)b * (p.A / 32 + 1);
+    const int ngrp = (Nc + 31) >> 5;
+
+    float t[kLaneTop];  // the lane's largest IoUs, descending (lists start at +0)
+#pragma unroll
+    for (int i = 0; i < kLaneTop; ++i) t[i] = 0.f;
+    int seen = 0;                                  // overlapping candidates of this lane
+    auto visit = [&](const bool valid, const float4 cc, const float ar) {
+        const float tlx = fmaxf(g_x1, cc.x), tly = fmaxf(g_y1, cc.y);
+        const float brx = fminf(g_x2, cc.z), bry = fminf(g_y2, cc.w);
+        if (valid && tlx < brx && tly < bry) {  // en == 1
+            ++seen;
+            const float area_i = (brx - tlx) * (bry - tly);
+            const float den = (area_a + ar) - area_i;
+            if (area_i >= (t[kLaneTop - 1] * den) * 0.999f) {
+                const float q = area_i / den;
+                lane_insert(t, q > t[kLaneTop - 1] ? q : 0.f);  // NaN / not above the lane's last: no-op
+            }
+        }
+    };
+    // Chunks of kSweepChunk groups: the GT's warps list the groups whose union box the GT overlaps (any order:
+    // only the IoU values matter), then walk the list together, 4 groups per warp and trip in flight.
+    for (int c0 = 0; c0 < ngrp; c0 += kSweepChunk) {
+        if (threadIdx.x % (kSweepSub * 32) == 0) s_nhit[gl] = 0;
+        gt_barrier(gl);
+        const int c1 = min(ngrp, c0 + kSweepChunk);
+        for (int q0 = c0 + ws * 32; q0 < c1; q0 += kSweepSub * 32) {
+            bool h = false;
+            if (q0 + lane < c1) {
+                const float4 u = __ldg(gb + q0 + lane);
+                h = fmaxf(g_x1, u.x) < fminf(g_x2, u.z) && fmaxf(g_y1, u.y) < fminf(g_y2, u.w);
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, h);
+            if (hit) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nhit[gl], __popc(hit));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (h) s_hit[gl][base + __popc(hit & ((1u << lane) - 1u))] = (unsigned short)(q0 + lane - c0);
+            }
+        }
+        gt_barrier(gl);
+        const int nhit = s_nhit[gl];
+        for (int i0 = ws * 4; i0 < nhit; i0 += kSweepSub * 4) {
+            bool ok[4];
+            float4 cc[4];
+            float ar[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ok[u] = i0 + u < nhit;
+                const int n = (c0 + (ok[u] ? (int)s_hit[gl][i0 + u] : 0)) * 32 + lane;
+                ok[u] = ok[u] && n < Nc;
+                cc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ar[u] = 0.f;
+                if (ok[u]) { cc[u] = __ldg(cb + n); ar[u] = __ldg(car + n); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u >= nhit) break;  // warp-uniform
+                visit(ok[u], cc[u], ar[u]);
+            }
+        }
+        if (c1 < ngrp) gt_barrier(gl);  // the list is rebuilt by the next pass
+    }
+    // ---- the GT's first warp collects the other warps' lane lists (same lane = same candidates modulo 32)
+    if (ws > 0) {
+#pragma unroll
+        for (int i = 0; i < kLaneTop; ++i) s_list[gl][ws - 1][i][lane] = t[i];
+        s_seen[gl][ws - 1][lane] = seen;
+    }
+    gt_barrier(gl);
+    if (ws > 0) return;
+#pragma unroll
+    for (int w = 0; w < kSweepSub - 1; ++w) {
+#pragma unroll
+        for (int u = 0; u < kLaneTop; ++u) lane_insert(t, s_list[gl][w][u][lane]);
+        seen += s_seen[gl][w][lane];
+    }
+    // ---- the 10 largest over all lanes: ten rounds of (warp max, pop it from the first lane holding it)
+    const float t_last = t[kLaneTop - 1];
+    float top = 0.f;  // lane i < 10: i-th largest
+    float m = 0.f;
+    for (int r = 0; r < 10; ++r) {
+        m = t[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == r) top = m;
+        const unsigned who = __ballot_sync(0xffffffffu, t[0] == m);
+        if (lane == __ffs(who) - 1) {
+#pragma unroll
+            for (int i = 0; i < kLaneTop - 1; ++i) t[i] = t[i + 1];
+            t[kLaneTop - 1] = -1.f;
+        }
+    }
+    // A lane that dropped candidates (saw more than it keeps) and whose last value still beats the 10th may have
+    // dropped a top-10 value.  Every candidate value above m (the 10th largest found) belongs to the true top 10,
+    // and at least 10 values are >= m: the exact list of the values above m, padded with m, is the answer.
+    const bool unsafe = seen > kLaneTop && t_last > m;
+    if (p.force_exact) top = sweep_exact(cb, car, gb, Nc, g_x1, g_y1, g_x2, g_y2, area_a, 0.f);
+    else if (__any_sync(0xffffffffu, unsafe)) top = sweep_exact(cb, car, gb, Nc, g_x1, g_y1, g_x2, g_y2, area_a, m);
+    // dynamic k = clamp(int(sum of the top min(10, Nc)), 1) with ATen's reduce tree (:336-340)
+    const int kc = min(10, Nc);
+    int bw = 1;
+    while (bw * 2 <= kc) bw <<= 1;
+    const float hi = __shfl_down_sync(0xffffffffu, top, bw);
+    float v = 0.f;
+    if (lane < bw) v = top + ((lane + bw < kc) ? hi : 0.f);
+    for (int h = bw >> 1; h >= 1; h >>= 1) {
+        const float o = __shfl_down_sync(0xffffffffu, v, h);
+        if (lane < h) v = v + o;
+    }
+    if (lane == 0) p.dyn_k[(size_t)b * p.Lmax + g] = max((int)v, 1);
 }
 
 // ---- K2 ------------------------------------------------------------------------------------
@@ -569,8 +727,6 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     const int gc = (int)L[0];  // .to(int64) truncates (:89)
     const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
     const int *ca = p.cand_anchor + (size_t)b * p.A;
-    const float4 *cb = p.cand_box + (size_t)b * p.A;
-    const float *car = p.cand_area + (size_t)b * p.A;
     // ATen picks a 64-wide block for sum(-1) when the [G,Nc] output has fewer than 16 elements (and C >= 64)
     const bool wide = (long long)G * Nc < 16 && p.C >= 64;
     if (tid == 0) sh.nconf = 0;
@@ -608,44 +764,15 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     }
 
     SPROF(1);
-    // ---- 1. the 10 largest IoUs of every GT: merge of the kSweepSplit slice lists (values only, :336-340)
+    // ---- 1. dynamic k of every GT (:336-340): computed by the IoU sweep
     SPROF(2);
-    if (half == 0 && live) {
-        float sv[3];  // 80 slice values, up to 3 per lane
-        const float *tp = p.top_part + ((size_t)b * p.Lmax + g) * kSweepSplit * 10;
-#pragma unroll
-        for (int u = 0; u < 3; ++u) sv[u] = (lane + 32 * u < kSweepSplit * 10) ? __ldg(tp + lane + 32 * u) : -1.f;
-        float top = 0.f;  // lane i < 10: i-th largest
-        for (int r = 0; r < 10; ++r) {
-            float m = fmaxf(sv[0], fmaxf(sv[1], sv[2]));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == r) top = fmaxf(m, 0.f);
-            // remove ONE instance of the maximum (equal values of different candidates are separate entries)
-            const bool mine = sv[0] == m || sv[1] == m || sv[2] == m;
-            const unsigned who = __ballot_sync(0xffffffffu, mine);
-            if (who && lane == __ffs(who) - 1) {
-                if (sv[0] == m) sv[0] = -1.f; else if (sv[1] == m) sv[1] = -1.f; else sv[2] = -1.f;
-            }
-        }
-        // dynamic k = clamp(int(sum of the top min(10, Nc)), 1) with ATen's reduce tree (:336-340)
-        const int kc = min(10, Nc);
-        int bw = 1;
-        while (bw * 2 <= kc) bw <<= 1;
-        const float hi = __shfl_down_sync(0xffffffffu, top, bw);
-        float v = 0.f;
-        if (lane < bw) v = top + ((lane + bw < kc) ? hi : 0.f);
-        for (int h = bw >> 1; h >= 1; h >>= 1) {
-            const float o = __shfl_down_sync(0xffffffffu, v, h);
-            if (lane < h) v = v + o;
-        }
-        const int k = max((int)__shfl_sync(0xffffffffu, v, 0), 1);
-        if (lane == 0) {
-            sh.k[gi] = k;
+    if (half == 0 && lane == 0) {
+        int k = 0;
+        if (live) {
+            k = __ldg(p.dyn_k + (size_t)b * p.Lmax + g);
             if (!(k < Nc - 1)) sh.nb[gi] = 0;  // quirk Q3: every candidate is taken, no cost needed
         }
-    } else if (half == 0 && lane == 0) {
-        sh.k[gi] = 0;
+        sh.k[gi] = k;
     }
     __syncthreads();
 
@@ -867,6 +994,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
 }
 
 static thread_local long long *g_sim_prof = nullptr;
+static thread_local int g_sim_force_exact = 0;
 
 static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, unsigned char *base) {
     size_t off = 0;
@@ -880,9 +1008,11 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
     const size_t o_sc = take((size_t)B * A * sizeof(unsigned));
     const size_t o_sm = take((size_t)B * A * sizeof(unsigned));
     const size_t o_rect = take((size_t)B * Lmax * n_levels * 8 * sizeof(short));
-    const size_t o_top = take((size_t)B * Lmax * kSweepSplit * 10 * sizeof(float));
+    const size_t o_gb = take((size_t)B * (A / 32 + 1) * sizeof(float4));
+    const size_t o_k = take((size_t)B * Lmax * sizeof(int));
     if (p) {
-        p->top_part = reinterpret_cast<float *>(base + o_top);
+        p->grp_box = reinterpret_cast<float4 *>(base + o_gb);
+        p->dyn_k = reinterpret_cast<int *>(base + o_k);
         p->meta = reinterpret_cast<int *>(base + o_meta);
         p->conf_list = reinterpret_cast<int *>(base + o_sl);
         p->res_iou = reinterpret_cast<float *>(base + o_ri);
@@ -901,6 +1031,9 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
 // debug hook (not part of include/plyolo.h): device buffer [B][ceil(Lmax/8)][16] of int64 for the match kernel's
 // phase timestamps (adds barriers: timing only), null switches it off
 extern "C" void plyolo_debug_simota_profile(void *device_buf) { plyolo::g_sim_prof = static_cast<long long *>(device_buf); }
+// debug hook: the IoU sweep uses its exact warp-wide top-10 list for every GT (normally only when the lane lists
+// cannot prove themselves exact) — lets the tests pin both routes
+extern "C" void plyolo_debug_simota_force_exact(int on) { plyolo::g_sim_force_exact = on; }
 
 extern "C" size_t plyolo_simota_workspace_bytes(int B, int A, int Lmax, int n_levels) {
     if (B < 1 || A < 1 || Lmax < 1 || n_levels < 1) return 0;
@@ -946,19 +1079,15 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     p.fg_mask = fg_mask; p.matched_gt = matched_gt; p.matched_iou = matched_iou; p.num_fg = num_fg; p.num_gt = num_gt;
     sim_ws_layout(B, A, Lmax, n_levels, &p, static_cast<unsigned char *>(workspace));
     p.prof = g_sim_prof;
+    p.force_exact = g_sim_force_exact;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t bm = (2 * (size_t)((A + 31) / 32) + 1) * sizeof(unsigned);
+    const size_t bm = (2 * (size_t)((A + 31) / 32) + 1 + (size_t)(A / kPrepSplit + 128)) * sizeof(unsigned);
     PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
     if (bm > 40 * 1024) cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm);
     record_stage_event(0, st);
     simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
-    const int slice_cap = ((((A + kSweepSplit - 1) / kSweepSplit) + 31) & ~31) + 32;
-    const size_t sweep_smem = (size_t)slice_cap * 20 + (size_t)(slice_cap / 32) * 16;
-    PLYOLO_REQUIRE(sweep_smem <= 200 * 1024, "A=%d too large for the IoU sweep's candidate slice", A);
-    if (sweep_smem > 48 * 1024)
-        cudaFuncSetAttribute(simota_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
-    simota_sweep_kernel<<<dim3(kSweepSplit * kSweepGtSplit, B), kSweepThreads, sweep_smem, st>>>(p, slice_cap);
+    simota_sweep_kernel<<<dim3((Lmax + kSweepGts - 1) / kSweepGts, B), kSweepThreads, 0, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_sweep_kernel");
     record_stage_event(1, st);
     cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));

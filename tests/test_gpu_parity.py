@@ -466,6 +466,40 @@ def test_simota_adversarial_edges_vs_oracle():
     assert_simota_equal(got, {k: v.cpu().numpy() for k, v in r.items()}, "replay adversarial")
 
 
+def test_simota_iou_sweep_routes():
+    """The IoU sweep's two routes (per-lane top-4 lists vs the exact warp-wide list) must agree with the oracle:
+    forced exact route on seeded inputs, and a construction where the 10 best candidates of a GT sit in the same
+    lane of consecutive candidate groups (the lane lists cannot hold them: automatic fallback)."""
+    import ctypes
+    L = _lib.lib()
+    L.plyolo_debug_simota_force_exact.argtypes = [ctypes.c_int]
+    size = 320
+    heads = synth.make_heads(4, size, 80, 21)
+    labels = synth.make_labels(4, size, 40, 80, 22)
+    dec, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    preds = dec.cpu().numpy()
+    o = oracle.simota(preds, labels, synth.level_shapes(size), STRIDES)
+    assert_simota_equal(run_simota(preds, labels, size), o, "lane-list route")
+    L.plyolo_debug_simota_force_exact(1)
+    try:
+        assert_simota_equal(run_simota(preds, labels, size), o, "forced exact route")
+    finally:
+        L.plyolo_debug_simota_force_exact(0)
+    # one GT covering the whole stride-8 level: every anchor is a candidate, candidate n == anchor n on level 0, so
+    # anchors 0, 32, 64, ... share a lane.  Their predictions are made near-perfect copies of the GT.
+    size = 160
+    heads = synth.make_heads(2, size, 80, 23, objects_per_image=0)
+    dec, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    preds = dec.cpu().numpy().copy()
+    lab = np.zeros((2, 4, 5), np.float32)
+    lab[:, 0] = [7, 80, 80, 158, 158]
+    lab[1, 1] = [9, 40, 40, 30, 30]
+    for j in range(12):
+        preds[:, 32 * j + 5, :4] = [80 + 0.01 * j, 80, 158 - 0.3 * j, 158]
+    o = oracle.simota(preds, lab, synth.level_shapes(size), STRIDES)
+    assert_simota_equal(run_simota(preds, lab, size), o, "same-lane top-10 (fallback)")
+
+
 def test_simota_small_class_counts():
     rng = np.random.default_rng(4)
     for C, shapes, strides in [(1, [(8, 8), (4, 4)], [8, 16]), (20, [(16, 16), (8, 8), (4, 4)], [8, 16, 32]), (33, [(16, 16)], [8])]:
