@@ -40,7 +40,7 @@ constexpr int kSweepGts = 2;      // GTs of one image per CTA
 constexpr int kSweepThreads = kSweepGts * kSweepSub * 32;
 constexpr int kSweepChunk = 1024;  // candidate groups listed per pass (all of them at 640^2)
 constexpr int kMaxBoth = 36 * PLYOLO_MAX_LEVELS;  // 5x5 centre cells per level (6x6 if an edge rounds outward)
-constexpr int kExtraEval = 4;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
+constexpr int kExtraEval = 1;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
 constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
 
 struct SimParams {
@@ -139,6 +139,28 @@ __device__ __forceinline__ void lane_terms(const RawRow &r, const int C, const i
     }
 }
 __device__ __forceinline__ float pos_term(const float p) { return -fmaxf(logf(p), -100.f); }  // target 1
+
+// Guaranteed lower bound of one negative BCE leaf -max(log1p(-p), -100), p = sqrt(sigmoid(x) * so) =
+// rsqrt((1 + e^-x) / so), from the hardware approximations (ex2, rsqrt; lg2 only for p > 0.3).  The relative error
+// of p stays below 2e-6, so for p <= 0.9 (|d leaf / d p| <= 10) the leaf of the approximate p is within 2e-5 of
+// the exact fp32 leaf; below 0.3 the truncated series p + p^2/2 + p^3/3 <= -log(1 - p) replaces the logarithm.
+// The result is that value minus 5e-5.  Above 0.9 the true leaf exceeds -log(0.1 + 1e-5) > 2.3: 2 is returned.
+// NaN -> 0.  inv_so = 1 / so (inf is fine: p = 0).
+__device__ __forceinline__ float neg_leaf_lower(const float x, const float inv_so) {
+    float e, pr;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));  // e^-x
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"((1.0f + e) * inv_so));
+    float n;
+    if (pr > 0.3f) {
+        if (pr > 0.9f) return 2.0f;
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f - pr));
+        n = l * -0.6931471805599453f;  // -log(1 - p)
+    } else {
+        n = pr + (pr * pr) * (0.5f + pr * 0.3333333f);
+    }
+    return n >= 5.0e-5f ? n - 5.0e-5f : 0.0f;
+}
 
 // ATen's strided accumulators for one lane: wide == false: 32 lanes ((e0+e1)+e2); wide == true: the
 // 64-lane block used when there are fewer than 16 outputs, folded to 32 lanes ((e0+e2)+(e1+0)).
@@ -703,10 +725,12 @@ struct MatchShared {
     int anchor[kGtPerCta][kMaxBoth];
     float cost[kGtPerCta][kMaxBoth];
     float iou[kGtPerCta][kMaxBoth];
+    float liou3[kGtPerCta][kMaxBoth];  // 3 * L_iou of the pair (exact)
+    float so[kGtPerCta][kMaxBoth];     // 1 / sigmoid(obj) of the pair's anchor
     float top[kMatchWarps][10];
     float terms[kMatchWarps][96];
     int conf[kMaxConf];
-    int k[kGtPerCta], nb[kGtPerCta];
+    int k[kGtPerCta], nb[kGtPerCta], gcls[kGtPerCta];
     int nconf, last, n_eval;
     unsigned short elist[kGtPerCta * kMaxBoth];    // (GT, anchor slot) pairs whose exact cost is wanted
     unsigned char state[kGtPerCta][kMaxBoth];      // 0 = lower bound only, 1 = queued, 2 = exact cost known
@@ -773,14 +797,15 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
             if (!(k < Nc - 1)) sh.nb[gi] = 0;  // quirk Q3: every candidate is taken, no cost needed
         }
         sh.k[gi] = k;
+        sh.gcls[gi] = gc;
     }
     __syncthreads();
 
     // ---- 2. cost of the in-both anchors (:84-108).  Only the k smallest costs of a GT matter, and
     //   cost = fl(fl(cls + 3 L_iou) + 0),  cls = ATen-ordered sum of 80 non-negative BCE leaves, one of them
     //   pos = -max(log p[gt class], -100):  every fp32 addition of non-negatives is monotone, so
-    //   lb = fl(fl(pos + 3 L_iou) + 0) <= cost, bit for bit.
-    // (a) lb for every pair, one thread each (6 floats of the row);  (b) exact cost — one warp per pair, the
+    //   lb = fl(fl(pos + S + 3 L_iou) + 0) <= cost for any S <= the sum of the other 79 leaves.
+    // (a) lb for every pair with S from fast-math leaves minus their error bound (tight: ~1e-3);  (b) exact cost — one warp per pair, the
     // expensive 80-class sweep — for the k pairs of smallest lb per GT;  (c) with U = the largest of those
     // exact costs, exact cost for every pair with lb <= U: all others cost more than k pairs already do.
     // The selection (3.) then runs over the exactly known costs only.
@@ -790,6 +815,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
 #pragma unroll
     for (int q = 0; q < kGtPerCta; ++q) pbase[q + 1] = pbase[q] + sh.nb[q];
     const int npairs = pbase[kGtPerCta];
+    // (a1) one thread per pair: the exact terms (positive leaf, IoU, 3 L_iou) from 6 floats of the row
     for (int t = tid; t < npairs; t += kMatchThreads) {
         int q = 0, base = 0;
 #pragma unroll
@@ -799,13 +825,52 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
         const float *row = p.preds + ((size_t)b * p.A + sh.anchor[q][i]) * p.ch;
         const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
         const int qc = (int)Lq[0];
+        const float so = sigmoid_ref(__ldg(row + 4));
         float pos = 0.f;
-        if (qc >= 0 && qc < p.C) pos = pos_term(sqrtf(sigmoid_ref(__ldg(row + 5 + qc)) * sigmoid_ref(__ldg(row + 4))));
+        if (qc >= 0 && qc < p.C) pos = pos_term(sqrtf(sigmoid_ref(__ldg(row + 5 + qc)) * so));
         const float iou = pair_iou(Lq[1], Lq[2], Lq[3], Lq[4], load_box(row));
         const float liou = -logf(iou + 1e-8f);
-        sh.cost[q][i] = (pos + 3.0f * liou) + 0.0f;
+        sh.cost[q][i] = pos;
+        sh.liou3[q][i] = 3.0f * liou;
+        sh.so[q][i] = 1.0f / so;
         sh.iou[q][i] = iou;
         sh.state[q][i] = 0;
+    }
+    __syncthreads();
+    {
+        // (a2) eight lanes per pair (four pairs per warp at a time, every class logit of the row loaded up front):
+        // S = guaranteed lower bound of the negative leaves' sum (neg_leaf_lower),
+        // lb = fl(fl((pos + S) (1 - 4e-6)) + 3 L_iou) — 4e-6 covers the fp32 roundings of the reference's 80-leaf
+        // tree sum (<= 8 half-ulps) and of this accumulation
+        constexpr int NJ = (PLYOLO_MAX_CLASSES + 7) / 8;
+        const int sub = lane & 7;
+        for (int t0 = warp * 4; t0 < npairs; t0 += kMatchWarps * 4) {
+            const int t = t0 + (lane >> 3);
+            const bool valid = t < npairs;
+            int q = 0, base = 0;
+#pragma unroll
+            for (int u = 1; u < kGtPerCta; ++u)
+                if (valid && t >= pbase[u]) { q = u; base = pbase[u]; }
+            const int i = valid ? t - base : 0;
+            const float *row = p.preds + ((size_t)b * p.A + (valid ? sh.anchor[q][i] : 0)) * p.ch + 5;
+            float x[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) x[j] = __ldg(row + min(sub + 8 * j, p.C - 1));  // unconditional: all in flight at once
+            const int qc = sh.gcls[q];
+            const float inv_so = sh.so[q][i];
+            float sneg = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int c = sub + 8 * j;
+                if (c < p.C && c != qc) sneg += neg_leaf_lower(x[j], inv_so);
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) sneg += __shfl_xor_sync(0xffffffffu, sneg, o);
+            if (valid && sub == 0) {
+                const float cl = (sh.cost[q][i] + sneg) * 0.999996f;
+                sh.cost[q][i] = (cl + sh.liou3[q][i]) + 0.0f;
+            }
+        }
     }
     if (tid == 0) sh.n_eval = 0;
     __syncthreads();
