@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kPpTile) score_kernel_simple(const ScoreParams
 // groups of 128 threads take the tiles round-robin, so the scoring latency of one tile (dependent max
 // chains, barriers, the bucket atomics) overlaps the next tiles' loads and compute.
 constexpr int kStages = 4;
-constexpr int kConsumers = 3;
+constexpr int kConsumers = 4;
 constexpr int kProducers = 2;  // producer warps (FUSED: each copies half of the channel rows)
 constexpr int kScoreThreads = 32 * kProducers + kPpTile * kConsumers;
 

@@ -33,13 +33,15 @@ namespace plyolo {
 constexpr int kPrepThreads = 512;
 constexpr int kPrepSplit = 4;     // CTAs per image in the prep kernel
 constexpr int kGtPerCta = 8;      // GTs per CTA in the match kernel
-constexpr int kMatchWarps = 16;   // two per GT during the IoU sweep
+constexpr int kMatchWarps = 16;  // two per GT during the IoU sweep
 constexpr int kMatchThreads = kMatchWarps * 32;
 constexpr int kSweepSub = 4;      // IoU sweep: warps per GT (each takes every 4th candidate group the GT overlaps)
 constexpr int kSweepGts = 2;      // GTs of one image per CTA
 constexpr int kSweepThreads = kSweepGts * kSweepSub * 32;
 constexpr int kSweepChunk = 1024;  // candidate groups listed per pass (all of them at 640^2)
 constexpr int kMaxBoth = 36 * PLYOLO_MAX_LEVELS;  // 5x5 centre cells per level (6x6 if an edge rounds outward)
+constexpr int kPrefetchRows = 2;  // L2 prefetch of the in-both anchors' prediction rows: 0 none, 1 first line, 2 whole row
+constexpr bool kTightAll = true;  // tight lower bounds for every pair up front (else: only for pairs the cheap bound cannot prune)
 constexpr int kExtraEval = 1;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
 constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
 
@@ -66,6 +68,7 @@ struct SimParams {
     short *rect;          // [B,Lmax,n_levels,8] in-box x0,x1,y0,y1 | in-centre x0,x1,y0,y1 (inclusive)
     float4 *grp_box;      // [B,A/32+1] union box of every group of 32 consecutive candidates
     int *dyn_k;           // [B,Lmax] dynamic k of every GT (:336-340)
+    int *gt_perm;         // [B,Lmax+8] match CTA c handles the GTs gt_perm[8c .. 8c+7] (-1 = none): balanced by #in-both anchors
     int force_exact;      // debug: the IoU sweep takes its exact warp-wide list for every GT
     long long *prof;      // debug: [B][gridDim.x][16] phase timestamps of the match kernel, or null
 };
@@ -140,26 +143,24 @@ __device__ __forceinline__ void lane_terms(const RawRow &r, const int C, const i
 }
 __device__ __forceinline__ float pos_term(const float p) { return -fmaxf(logf(p), -100.f); }  // target 1
 
-// Guaranteed lower bound of one negative BCE leaf -max(log1p(-p), -100), p = sqrt(sigmoid(x) * so) =
-// rsqrt((1 + e^-x) / so), from the hardware approximations (ex2, rsqrt; lg2 only for p > 0.3).  The relative error
-// of p stays below 2e-6, so for p <= 0.9 (|d leaf / d p| <= 10) the leaf of the approximate p is within 2e-5 of
-// the exact fp32 leaf; below 0.3 the truncated series p + p^2/2 + p^3/3 <= -log(1 - p) replaces the logarithm.
-// The result is that value minus 5e-5.  Above 0.9 the true leaf exceeds -log(0.1 + 1e-5) > 2.3: 2 is returned.
-// NaN -> 0.  inv_so = 1 / so (inf is fine: p = 0).
-__device__ __forceinline__ float neg_leaf_lower(const float x, const float inv_so) {
+// One negative BCE leaf -max(log1p(-p), -100), p = sqrt(sigmoid(x) * so) = rsqrt(1/so + e^-x / so), from the
+// hardware approximations (ex2, rsqrt; lg2 only for p > 0.3), within kLeafErr of the exact fp32 leaf or below it:
+// the relative error of p stays below 2e-6, so for p <= 0.9 (|d leaf / d p| <= 10) the leaf of the approximate p is
+// within 2e-5 of the exact one; below 0.3 the truncated series p + p^2/2 + p^3/3 <= -log(1 - p) replaces the
+// logarithm; above 0.9 the true leaf exceeds -log(0.1 + 1e-5) > 2.3 and 2 is returned.
+// inv_so = 1 / so, lso = log2(inv_so) (inf is fine: p = 0).  Explicit fma: this is a bound, not reference arithmetic.
+constexpr float kLeafErr = 5.0e-5f;
+__device__ __forceinline__ float neg_leaf_approx(const float x, const float inv_so, const float lso) {
     float e, pr;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));  // e^-x
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"((1.0f + e) * inv_so));
-    float n;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(x, -1.4426950408889634f, lso)));  // e^-x / so
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"(inv_so + e));
     if (pr > 0.3f) {
         if (pr > 0.9f) return 2.0f;
         float l;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f - pr));
-        n = l * -0.6931471805599453f;  // -log(1 - p)
-    } else {
-        n = pr + (pr * pr) * (0.5f + pr * 0.3333333f);
+        return l * -0.6931471805599453f;  // -log(1 - p)
     }
-    return n >= 5.0e-5f ? n - 5.0e-5f : 0.0f;
+    return __fmaf_rn(pr * pr, __fmaf_rn(pr, 0.3333333f, 0.5f), pr);
 }
 
 // ATen's strided accumulators for one lane: wide == false: 32 lanes ((e0+e1)+e2); wide == true: the
@@ -230,7 +231,7 @@ __device__ __forceinline__ void set_bits(unsigned *bitmap, const int p0, const i
 }
 
 __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimParams p) {
-    extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1] | this CTA's candidates [A/4 + 128]
+    extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1] | this CTA's candidates [A/4 + 128] | in-both count per GT [Lmax]
     __shared__ int s_G, s_warp[kPrepThreads / 32];
     const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (p.A + 31) >> 5;
@@ -256,6 +257,11 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
     __syncthreads();
     const int G = s_G;  // the GTs are rows [0, G) (:64-65)
 
+    int *s_nb = reinterpret_cast<int *>(prep_smem) + 2 * nwords + 1 + (p.A / kPrepSplit + 128);  // [Lmax] (CTA 0 only)
+    if (q == 0) {
+        for (int g = tid; g < p.Lmax; g += kPrepThreads) s_nb[g] = 0;
+        __syncthreads();
+    }
     // geometry prior: one work item per (GT, level)
     const int items = G * p.n_levels;
     for (int it = tid; it < items; it += kPrepThreads) {
@@ -274,6 +280,10 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
             r8[0] = (short)bx0; r8[1] = (short)bx1; r8[2] = (short)by0; r8[3] = (short)by1;
             r8[4] = (short)cx0; r8[5] = (short)cx1; r8[6] = (short)cy0; r8[7] = (short)cy1;
         }
+        if (q == 0) {  // in-box AND in-centre cells of this level: the match kernel's cost pairs of the GT
+            const int ix0 = max(bx0, cx0), ix1 = min(bx1, cx1), iy0 = max(by0, cy0), iy1 = min(by1, cy1);
+            if (ix0 <= ix1 && iy0 <= iy1) atomicAdd(&s_nb[g], (ix1 - ix0 + 1) * (iy1 - iy0 + 1));
+        }
         const int o = p.off[l];
         if (bx0 <= bx1)
             for (int y = by0; y <= by1; ++y) set_bits(bm_fg, o + y * W + bx0, o + y * W + bx1);
@@ -281,6 +291,26 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
             for (int y = cy0; y <= cy1; ++y) set_bits(bm_fg, o + y * W + cx0, o + y * W + cx1);
     }
     __syncthreads();
+
+    if (q == 0) {
+        // Load balance of the match kernel: its CTA c takes the GTs gt_perm[8c .. 8c+7].  GTs sorted by their
+        // number of in-both anchors (descending, ties by index) are dealt to the ceil(G/8) CTAs in snake order.
+        const int ncta = (G + kGtPerCta - 1) / kGtPerCta;
+        int *perm = p.gt_perm + (size_t)b * (p.Lmax + kGtPerCta);
+        for (int i = tid; i < ncta * kGtPerCta; i += kPrepThreads) perm[i] = -1;
+        __syncthreads();
+        for (int g = tid; g < G; g += kPrepThreads) {
+            const int nbg = s_nb[g];
+            int r = 0;
+            for (int h = 0; h < G; ++h) {
+                const int nbh = s_nb[h];
+                r += (nbh > nbg || (nbh == nbg && h < g)) ? 1 : 0;
+            }
+            const int round = r / ncta, pos = r - round * ncta;
+            const int c = (round & 1) ? ncta - 1 - pos : pos;
+            perm[c * kGtPerCta + round] = g;
+        }
+    }
 
     // exclusive prefix of the word popcounts: candidate n <-> n-th set bit of fg (:79-82)
     int run = 0;  // same value in every thread
@@ -726,12 +756,16 @@ struct MatchShared {
     float cost[kGtPerCta][kMaxBoth];
     float iou[kGtPerCta][kMaxBoth];
     float liou3[kGtPerCta][kMaxBoth];  // 3 * L_iou of the pair (exact)
+    float pos[kGtPerCta][kMaxBoth];    // positive BCE leaf of the pair (exact)
     float so[kGtPerCta][kMaxBoth];     // 1 / sigmoid(obj) of the pair's anchor
+    float lso[kGtPerCta][kMaxBoth];    // log2 of it
     float top[kMatchWarps][10];
     float terms[kMatchWarps][96];
     int conf[kMaxConf];
-    int k[kGtPerCta], nb[kGtPerCta], gcls[kGtPerCta];
-    int nconf, last, n_eval;
+    int k[kGtPerCta], nb[kGtPerCta], gcls[kGtPerCta], gidx[kGtPerCta];
+    int nconf, last, n_eval, n_cand;
+    unsigned ucut[kGtPerCta];                      // ordered(U): the k-th smallest exact cost after the first round
+    unsigned short clist[kGtPerCta * kMaxBoth];    // pairs whose cheap lower bound does not exceed U
     unsigned short elist[kGtPerCta * kMaxBoth];    // (GT, anchor slot) pairs whose exact cost is wanted
     unsigned char state[kGtPerCta][kMaxBoth];      // 0 = lower bound only, 1 = queued, 2 = exact cost known
 };
@@ -745,9 +779,10 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     if (g0 >= G || Nc == 0) return;
     const int n_active = (G + kGtPerCta - 1) / kGtPerCta;  // CTAs of this image that reach the end
     const int gi = warp & (kGtPerCta - 1), half = warp / kGtPerCta;  // IoU sweep: GT and candidate half of this warp
-    const int g = g0 + gi;
-    const bool live = g < G;
-    const float *L = p.labels + ((size_t)b * p.Lmax + (live ? g : g0)) * 5;
+    const int *perm = p.gt_perm + (size_t)b * (p.Lmax + kGtPerCta) + g0;  // this CTA's GTs (balanced by prep)
+    const int g = __ldg(perm + gi);
+    const bool live = g >= 0;
+    const float *L = p.labels + ((size_t)b * p.Lmax + (live ? g : 0)) * 5;
     const int gc = (int)L[0];  // .to(int64) truncates (:89)
     const float gx = L[1], gy = L[2], gw = L[3], gh = L[4];
     const int *ca = p.cand_anchor + (size_t)b * p.A;
@@ -775,10 +810,12 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
                         const int a = p.off[l] + (y0 + i / wx) * p.w[l] + x0 + i % wx;
                         sh.anchor[gi][nb + i] = a;
                         const char *row = reinterpret_cast<const char *>(p.preds + ((size_t)b * p.A + a) * p.ch);
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 256));
-                        if (p.ch * 4 > 384 - 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + p.ch * 4 - 4));
+                        if (kPrefetchRows >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                        if (kPrefetchRows >= 2) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 256));
+                            if (p.ch * 4 > 384 - 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + p.ch * 4 - 4));
+                        }
                     }
                 }
                 nb = min(nb + cells, kMaxBoth);
@@ -798,6 +835,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
         }
         sh.k[gi] = k;
         sh.gcls[gi] = gc;
+        sh.gidx[gi] = live ? g : 0;
     }
     __syncthreads();
 
@@ -823,56 +861,77 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
             if (t >= pbase[u]) { q = u; base = pbase[u]; }
         const int i = t - base;
         const float *row = p.preds + ((size_t)b * p.A + sh.anchor[q][i]) * p.ch;
-        const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
+        const float *Lq = p.labels + ((size_t)b * p.Lmax + sh.gidx[q]) * 5;
         const int qc = (int)Lq[0];
         const float so = sigmoid_ref(__ldg(row + 4));
         float pos = 0.f;
         if (qc >= 0 && qc < p.C) pos = pos_term(sqrtf(sigmoid_ref(__ldg(row + 5 + qc)) * so));
         const float iou = pair_iou(Lq[1], Lq[2], Lq[3], Lq[4], load_box(row));
         const float liou = -logf(iou + 1e-8f);
-        sh.cost[q][i] = pos;
+        sh.pos[q][i] = pos;
         sh.liou3[q][i] = 3.0f * liou;
+        sh.cost[q][i] = (pos + 3.0f * liou) + 0.0f;  // lb0: the negative leaves are >= 0
         sh.so[q][i] = 1.0f / so;
+        sh.lso[q][i] = log2f(1.0f / so);
         sh.iou[q][i] = iou;
         sh.state[q][i] = 0;
+        if (kTightAll) sh.clist[t] = (unsigned short)(q * kMaxBoth + i);
     }
-    __syncthreads();
-    {
-        // (a2) eight lanes per pair (four pairs per warp at a time, every class logit of the row loaded up front):
-        // S = guaranteed lower bound of the negative leaves' sum (neg_leaf_lower),
-        // lb = fl(fl((pos + S) (1 - 4e-6)) + 3 L_iou) — 4e-6 covers the fp32 roundings of the reference's 80-leaf
-        // tree sum (<= 8 half-ulps) and of this accumulation
+    // Tight lower bound of the listed pairs sh.clist[0, ncand) — eight lanes per pair, four pairs per warp at a
+    // time, every class logit of the row loaded up front:
+    // S = guaranteed lower bound of the negative leaves' sum (neg_leaf_approx minus its error bound),
+    // lb = fl(fl((pos + S) (1 - 4e-6)) + 3 L_iou) — 4e-6 covers the fp32 roundings of the reference's 80-leaf
+    // tree sum (<= 8 half-ulps) and of this accumulation.  filter: pairs with lb <= U are queued for the exact
+    // evaluation, the others leave the selection; !filter: lb replaces the cheap bound.
+    auto tight_pass = [&](const int ncand, const bool filter) {
         constexpr int NJ = (PLYOLO_MAX_CLASSES + 7) / 8;
         const int sub = lane & 7;
-        for (int t0 = warp * 4; t0 < npairs; t0 += kMatchWarps * 4) {
+        for (int t0 = warp * 4; t0 < ncand; t0 += kMatchWarps * 4) {
             const int t = t0 + (lane >> 3);
-            const bool valid = t < npairs;
-            int q = 0, base = 0;
-#pragma unroll
-            for (int u = 1; u < kGtPerCta; ++u)
-                if (valid && t >= pbase[u]) { q = u; base = pbase[u]; }
-            const int i = valid ? t - base : 0;
+            const bool valid = t < ncand;
+            const int e = valid ? sh.clist[t] : 0;
+            const int q = e / kMaxBoth, i = e % kMaxBoth;
             const float *row = p.preds + ((size_t)b * p.A + (valid ? sh.anchor[q][i] : 0)) * p.ch + 5;
             float x[NJ];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) x[j] = __ldg(row + min(sub + 8 * j, p.C - 1));  // unconditional: all in flight at once
             const int qc = sh.gcls[q];
-            const float inv_so = sh.so[q][i];
+            const float inv_so = sh.so[q][i], lso = sh.lso[q][i];
             float sneg = 0.f;
+            int nleaf = 0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                const int c = sub + 8 * j;
-                if (c < p.C && c != qc) sneg += neg_leaf_lower(x[j], inv_so);
+                if (8 * j < p.C) {  // uniform
+                    const int c = sub + 8 * j;
+                    const float n = neg_leaf_approx(x[j], inv_so, lso);
+                    const bool use = c < p.C && c != qc;
+                    sneg += use ? n : 0.f;
+                    nleaf += use ? 1 : 0;
+                }
             }
+            sneg = sneg - (float)nleaf * kLeafErr;  // every exact leaf is >= max(approximation - kLeafErr, 0)
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) sneg += __shfl_xor_sync(0xffffffffu, sneg, o);
+            if (!(sneg >= 0.f)) sneg = 0.f;  // also NaN
             if (valid && sub == 0) {
-                const float cl = (sh.cost[q][i] + sneg) * 0.999996f;
-                sh.cost[q][i] = (cl + sh.liou3[q][i]) + 0.0f;
+                const float cl = (sh.pos[q][i] + sneg) * 0.999996f;
+                const float lb = (cl + sh.liou3[q][i]) + 0.0f;
+                if (!filter) {
+                    sh.cost[q][i] = lb;
+                } else if (float_ordered(lb) <= sh.ucut[q]) {
+                    sh.state[q][i] = 1;
+                    sh.elist[atomicAdd(&sh.n_eval, 1)] = (unsigned short)e;
+                } else {
+                    sh.cost[q][i] = __int_as_float(0x7fc00000);  // cannot be among the k smallest: out of the selection
+                }
             }
         }
+    };
+    if (kTightAll) {
+        __syncthreads();
+        tight_pass(npairs, false);
     }
-    if (tid == 0) sh.n_eval = 0;
+    if (tid == 0) { sh.n_eval = 0; sh.n_cand = 0; }
     __syncthreads();
     // exact cost of every queued pair: the warps walk the list with stride 16, loading the NEXT pair's
     // prediction row (three coalesced requests) before evaluating the current one
@@ -891,7 +950,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
                 qn = sh.elist[t + kMatchWarps] / kMaxBoth; in_ = sh.elist[t + kMatchWarps] % kMaxBoth;
                 load_row(p.preds + ((size_t)b * p.A + sh.anchor[qn][in_]) * p.ch, p.C, lane, nxt);
             }
-            const float *Lq = p.labels + ((size_t)b * p.Lmax + g0 + q) * 5;
+            const float *Lq = p.labels + ((size_t)b * p.Lmax + sh.gidx[q]) * 5;
             float iou;
             const float c = pair_cost_row(p, cur, Lq[1], Lq[2], Lq[3], Lq[4], (int)Lq[0], true, wide, lane, sh.terms[warp], &iou);
             if (lane == 0) { sh.cost[q][i] = c; sh.state[q][i] = 2; }
@@ -953,16 +1012,23 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
             floor_ = (unsigned)(best & 0xffffffffu);
             first = false;
         }
+        if (lane == 0) sh.ucut[gi] = umax;
         for (int i = lane; i < nb; i += 32)
             if (sh.state[gi][i] == 0) {
                 if (float_ordered(sh.cost[gi][i]) <= umax) {
-                    sh.state[gi][i] = 1;
-                    sh.elist[atomicAdd(&sh.n_eval, 1)] = (unsigned short)(gi * kMaxBoth + i);
+                    if (kTightAll) {
+                        sh.state[gi][i] = 1;
+                        sh.elist[atomicAdd(&sh.n_eval, 1)] = (unsigned short)(gi * kMaxBoth + i);
+                    } else {
+                        sh.clist[atomicAdd(&sh.n_cand, 1)] = (unsigned short)(gi * kMaxBoth + i);
+                    }
                 } else {
                     sh.cost[gi][i] = __int_as_float(0x7fc00000);  // cannot be among the k smallest: out of the selection
                 }
             }
     }
+    __syncthreads();
+    if (!kTightAll) tight_pass(sh.n_cand, true);
     __syncthreads();
     SPROF(7);
     evaluate_queued();
@@ -1075,9 +1141,11 @@ static size_t sim_ws_layout(int B, int A, int Lmax, int n_levels, SimParams *p, 
     const size_t o_rect = take((size_t)B * Lmax * n_levels * 8 * sizeof(short));
     const size_t o_gb = take((size_t)B * (A / 32 + 1) * sizeof(float4));
     const size_t o_k = take((size_t)B * Lmax * sizeof(int));
+    const size_t o_perm = take((size_t)B * (Lmax + kGtPerCta) * sizeof(int));
     if (p) {
         p->grp_box = reinterpret_cast<float4 *>(base + o_gb);
         p->dyn_k = reinterpret_cast<int *>(base + o_k);
+        p->gt_perm = reinterpret_cast<int *>(base + o_perm);
         p->meta = reinterpret_cast<int *>(base + o_meta);
         p->conf_list = reinterpret_cast<int *>(base + o_sl);
         p->res_iou = reinterpret_cast<float *>(base + o_ri);
@@ -1146,7 +1214,7 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     p.prof = g_sim_prof;
     p.force_exact = g_sim_force_exact;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t bm = (2 * (size_t)((A + 31) / 32) + 1 + (size_t)(A / kPrepSplit + 128)) * sizeof(unsigned);
+    const size_t bm = (2 * (size_t)((A + 31) / 32) + 1 + (size_t)(A / kPrepSplit + 128) + (size_t)Lmax) * sizeof(unsigned);
     PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
     if (bm > 40 * 1024) cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm);
     record_stage_event(0, st);

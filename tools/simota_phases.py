@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 L.plyolo_debug_simota_profile(None)
 p = prof.cpu().numpy().reshape(-1, 16)
 p = p[p[:, 0] != 0]
-names = ["both lists", "(none)", "merge top10 / k", "lower bounds", "queue k", "eval 1", "queue <=U", "eval 2", "select+claim", "conflicts", "finalize", "-"]
+names = ["in-both lists", "(none)", "dynamic k", "cheap bounds", "queue k", "eval 1", "U, tight bounds", "eval 2", "select+claim", "conflicts", "finalize", "-"]
 d = np.diff(p[:, :12], axis=1) / 1965.0
 print("active CTAs", len(p), " phase us: mean / max")
 for i, n in enumerate(names[:11]):
