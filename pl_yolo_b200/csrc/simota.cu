@@ -144,23 +144,27 @@ __device__ __forceinline__ void lane_terms(const RawRow &r, const int C, const i
 __device__ __forceinline__ float pos_term(const float p) { return -fmaxf(logf(p), -100.f); }  // target 1
 
 // One negative BCE leaf -max(log1p(-p), -100), p = sqrt(sigmoid(x) * so) = rsqrt(1/so + e^-x / so), from the
-// hardware approximations (ex2, rsqrt; lg2 only for p > 0.3), within kLeafErr of the exact fp32 leaf or below it:
+// hardware approximations (ex2, rsqrt; lg2 only when some p > 0.3), within kLeafErr of the exact fp32 leaf or below it:
 // the relative error of p stays below 2e-6, so for p <= 0.9 (|d leaf / d p| <= 10) the leaf of the approximate p is
 // within 2e-5 of the exact one; below 0.3 the truncated series p + p^2/2 + p^3/3 <= -log(1 - p) replaces the
 // logarithm; above 0.9 the true leaf exceeds -log(0.1 + 1e-5) > 2.3 and 2 is returned.
 // inv_so = 1 / so, lso = log2(inv_so) (inf is fine: p = 0).  Explicit fma: this is a bound, not reference arithmetic.
 constexpr float kLeafErr = 5.0e-5f;
-__device__ __forceinline__ float neg_leaf_approx(const float x, const float inv_so, const float lso) {
+// p of one leaf (branch-free: the leaves of a row are independent chains)
+__device__ __forceinline__ float leaf_p_approx(const float x, const float inv_so, const float lso) {
     float e, pr;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(x, -1.4426950408889634f, lso)));  // e^-x / so
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"(inv_so + e));
-    if (pr > 0.3f) {
-        if (pr > 0.9f) return 2.0f;
-        float l;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f - pr));
-        return l * -0.6931471805599453f;  // -log(1 - p)
-    }
+    return pr;
+}
+__device__ __forceinline__ float leaf_series(const float pr) {  // p + p^2/2 + p^3/3 <= -log(1 - p)
     return __fmaf_rn(pr * pr, __fmaf_rn(pr, 0.3333333f, 0.5f), pr);
+}
+__device__ __forceinline__ float leaf_general(const float pr) {  // any p: series, logarithm or the constant
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f - pr));
+    const float n = pr > 0.3f ? l * -0.6931471805599453f : leaf_series(pr);
+    return pr > 0.9f ? 2.0f : n;
 }
 
 // ATen's strided accumulators for one lane: wide == false: 32 lanes ((e0+e1)+e2); wide == true: the
@@ -879,7 +883,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     }
     // Tight lower bound of the listed pairs sh.clist[0, ncand) — eight lanes per pair, four pairs per warp at a
     // time, every class logit of the row loaded up front:
-    // S = guaranteed lower bound of the negative leaves' sum (neg_leaf_approx minus its error bound),
+    // S = guaranteed lower bound of the negative leaves' sum (leaf_p_approx + leaf_series minus kLeafErr per leaf),
     // lb = fl(fl((pos + S) (1 - 4e-6)) + 3 L_iou) — 4e-6 covers the fp32 roundings of the reference's 80-leaf
     // tree sum (<= 8 half-ulps) and of this accumulation.  filter: pairs with lb <= U are queued for the exact
     // evaluation, the others leave the selection; !filter: lb replaces the cheap bound.
@@ -897,17 +901,29 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
             for (int j = 0; j < NJ; ++j) x[j] = __ldg(row + min(sub + 8 * j, p.C - 1));  // unconditional: all in flight at once
             const int qc = sh.gcls[q];
             const float inv_so = sh.so[q][i], lso = sh.lso[q][i];
-            float sneg = 0.f;
+            float sneg = 0.f, pmax = 0.f;
             int nleaf = 0;
+            float pr[NJ];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
+                pr[j] = 0.f;
                 if (8 * j < p.C) {  // uniform
                     const int c = sub + 8 * j;
-                    const float n = neg_leaf_approx(x[j], inv_so, lso);
                     const bool use = c < p.C && c != qc;
-                    sneg += use ? n : 0.f;
+                    const float v = leaf_p_approx(x[j], inv_so, lso);
+                    pr[j] = use ? v : 0.f;  // p = 0: leaf 0 in either formula
                     nleaf += use ? 1 : 0;
+                    pmax = fmaxf(pmax, pr[j]);
                 }
+            }
+            if (!__any_sync(0xffffffffu, pmax > 0.3f)) {  // the usual case: every leaf by the series, no branches
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (8 * j < p.C) sneg += leaf_series(pr[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    if (8 * j < p.C) sneg += leaf_general(pr[j]);
             }
             sneg = sneg - (float)nleaf * kLeafErr;  // every exact leaf is >= max(approximation - kLeafErr, 0)
 #pragma unroll
