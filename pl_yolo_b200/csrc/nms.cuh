@@ -893,9 +893,10 @@ constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a t
 //      a chunk tests its boxes against the keeps of every earlier chunk of its class as soon as that
 //      chunk is final (flag in shared memory), then settles its own 32 boxes and publishes its keeps —
 //      the chunks of a class pipeline across warps and only the settle step is serial;
-//   4. kept keys compacted, block-sorted, the first max_det published as records (key, box, score, class).
-// The image's last CTA to finish merges the kGroups sorted lists by rank (binary searches) and writes
-// the first max_det rows.  Anything else — and any image where a cross-class pair suppresses — is
+//   4. kept keys compacted (sorted and cut to max_det only when a group keeps more than that).
+// The kGroups CTAs of an image form one thread-block cluster: after a cluster barrier every CTA copies the other
+// groups' kept keys through distributed shared memory, ranks its own keys among all of them by counting
+// (rank = output row) and writes its rows.  Anything else — and any image where a cross-class pair suppresses — is
 // handled by one CTA with nms_image (exact general algorithm).
 __global__ void __cluster_dims__(kGroups, 1, 1) __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];

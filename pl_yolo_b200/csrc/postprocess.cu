@@ -1,22 +1,19 @@
 // postprocess.cu — confidence filter + class-aware NMS (models/evaluators/postprocess.py:7-48,
 // tv:ops/boxes.py:51-120, torchvision::nms), from materialised predictions or fused with the decode.
 //
-// Stage 1  score_kernel<FUSED>   one CTA per tile of 128 anchors, HBM-bound.
-//   The tile lands in shared memory through the TMA engine's 1-D bulk copies
-//   (cp.async.bulk + mbarrier, no register staging):
-//     FUSED : 5+C row copies of 512 B from the channel-planar head maps  -> tile[channel][anchor]
-//     preds : one contiguous copy of 128*(5+C) floats                     -> tile[anchor][channel]
-//   Pass A (thread per anchor): sigmoid(obj), max raw class logit, a conservative pre-filter that can
-//   only over-admit.  Pass B (4 lanes per admitted anchor): exact max / first argmax over the
-//   sigmoid VALUES (T1), conf = sigmoid(obj) * class_conf, conf >= thr in fp32.  The survivors are
-//   compacted IN ANCHOR ORDER (warp ballot + prefix) into the tile's slot range of the candidate arrays.
-// Stage 2  nms_kernel            one CTA per image, latency-bound.
-//   tile counts -> prefix -> the first max_nms candidates in anchor order (T2) -> 64-bit keys
-//   (~ordered(score) << 32 | slot) -> bitonic sort (register/shuffle steps inside warps, shared
-//   memory only for distances >= 64) == stable descending sort -> greedy NMS in rounds of 128
-//   candidates against the kept list (<= max_det, early exit: output order == score order == sweep
-//   order) with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division;
-//   see `suppresses`).
+// Stage 1  score_kernel<FUSED>   persistent, one CTA per SM, HBM-bound.
+//   A producer warp streams tiles of 128 anchors into a 4-stage shared-memory ring through the TMA engine
+//   (FUSED: one 2-D tensor-map request per tile = 5+C channel-plane rows of 512 B -> tile[channel][anchor], L2
+//   evict-first; preds: one contiguous bulk copy -> tile[anchor][channel]); four consumer groups of 128 threads
+//   score them (thread per anchor): sigmoid(obj); the largest raw class logit from three-input maxima over chunks
+//   of 16 classes; a conservative pre-filter that can only over-admit; for the admitted anchors the exact max /
+//   first argmax over the sigmoid VALUES (T1) inside the rounding window of the fp32 sigmoid;
+//   conf = sigmoid(obj) * class_conf, conf >= thr in fp32.  The survivors are compacted IN ANCHOR ORDER (warp
+//   ballot + prefix) into the tile's slot range of the candidate arrays and bucketed by class group.
+// Stage 2  nms_group_kernel      one 4-CTA cluster per image (nms.cuh), latency-bound: per-class sorts and greedy
+//   sweeps with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division; see
+//   `suppresses`), kept lists merged by rank through distributed shared memory; nms_image (one CTA, global sort +
+//   bit-matrix rounds) for everything the class split cannot handle exactly.
 #include <cstring>
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
@@ -329,7 +326,7 @@ __global__ void __launch_bounds__(kPpTile) score_kernel_simple(const ScoreParams
 // tile it waits for a free stage and copies the tile asynchronously onto the stage's mbarrier — from the
 // channel-planar head maps with 16-byte cp.async (one 512 B row per warp instruction: the TMA engine's
 // per-request service time caps 512 B bulk copies near 3 TB/s chip-wide, measured), from preds with one
-// contiguous TMA bulk copy of the whole tile.  Three consumer
+// contiguous TMA bulk copy of the whole tile.  kConsumers consumer
 // groups of 128 threads take the tiles round-robin, so the scoring latency of one tile (dependent max
 // chains, barriers, the bucket atomics) overlaps the next tiles' loads and compute.
 constexpr int kStages = 4;
@@ -430,7 +427,7 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
             const int t = tile_of(seq);
             if (t >= total) break;
             const int s = seq % kStages, k = seq / kStages;
-            // Stage s is consumed by a different group every time (3 groups, 4 stages), and an mbarrier wait only
+            // Stage s may be consumed by a different group every time (kConsumers vs kStages), and an mbarrier wait only
             // knows the phase PARITY: waiting for fill k while fill k-1 has not even landed would return at
             // once.  The stage's release k-1 (which implies fill k-1 completed and was consumed; release k-2 is
             // already implied by this group's own progress) is therefore awaited first.

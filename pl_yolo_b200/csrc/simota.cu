@@ -9,20 +9,20 @@
 //     quarter of the anchors: background defaults of the outputs, ordered compaction of the
 //     candidates (candidate n <-> n-th set bit, :79-82) and the gather of their corner boxes / areas
 //     (16 of the 340 bytes of each prediction row) for the IoU sweep.
-//  K2a simota_sweep_kernel    32 CTAs per image: (candidate slice, quarter of the GTs)
-//     top-10 IoU values (:336-340) of every GT inside every slice; groups of 32 candidates whose
-//     union box misses the GT are skipped (their IoU is 0).
-//  K2b simota_match_kernel    one CTA (16 warps) per 8 GTs of an image
-//     1. merge of the slice lists -> dynamic k with ATen's reduce tree;
-//     2. cost (:84-108) only for the <= 25 * levels anchors that are both in-box and in-centre (every
+//  K2a simota_sweep_kernel    4 warps per GT
+//     top-10 IoU values (:336-340) of every GT -> dynamic k; groups of 32 candidates whose union box misses the GT
+//     are skipped (their IoU is 0); per-lane top-6 lists, exact fallback when they cannot prove themselves.
+//  K2b simota_match_kernel    one CTA (16 warps) per 8 GTs of an image (dealt by prep: balanced by #in-both anchors)
+//     1. cost (:84-108) only for the <= 25 * levels anchors that are both in-box and in-centre (every
 //        other cost carries +1e5, so the k smallest live there unless the GT is tiny), and of those
-//        only the pairs that can still be among the k smallest: a bit-exact lower bound (positive BCE
-//        leaf + IoU term) prunes the expensive 80-class sweep (one warp per pair, ATen's CUDA reduce
-//        order: lane t adds classes t, t+32, t+64, then a halving tree);
-//     3. k smallest (cost, anchor) per GT -> per-anchor match count / tentative match by atomics;
+//        only the pairs that can still be among the k smallest: a rigorous tight lower bound (exact positive BCE
+//        leaf + IoU term + hardware-approximation negative leaves minus their error bound) prunes the expensive
+//        80-class sweep (one warp per pair, ATen's CUDA reduce order: lane t adds classes t, t+32, t+64, then a
+//        halving tree) to about k + 1 pairs per GT;
+//     2. k smallest (cost, anchor) per GT -> per-anchor match count / tentative match by atomics;
 //        anchors claimed twice are resolved right away by the argmin of the cost over ALL GTs
 //        (:352-356, quirk Q4);
-//     4. the image's last CTA to finish patches the resolved matches over the tentative ones and
+//     3. the image's last CTA to finish patches the resolved matches over the tentative ones and
 //        publishes num_fg (:357-369).
 #include <cfloat>
 
