@@ -135,6 +135,33 @@ int plyolo_bboxes_iou_f32(const float *a, int na, const float *b, int nb, int xy
 int plyolo_format_dets_f32(const float *dets, const int32_t *counts, const float *inv_scales, int B, int max_det,
                            float *out, plyolo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * loss tail of YOLOXLoss (N2) — replaces models/losses/yolox/yolox_loss.py:121-163 for use_l1 == False: the
+ * per-image target building (:123-127, :142-147), IOUloss(loss_type="giou")
+ * (models/layers/losses/iou_loss.py:7-50) on the foreground anchors, BCEWithLogitsLoss on the objectness of
+ * all B*A anchors (:152) and on the classes of the foreground anchors (:154).
+ *   preds, labels            as for plyolo_simota_f32
+ *   fg_mask, matched_gt, matched_iou   the outputs of plyolo_simota_f32
+ *   sums   [3] fp32 device: sum of the GIoU losses, of the objectness BCE terms, of the class BCE terms
+ *          (the reference's loss_iou / loss_obj / loss_cls are these divided by max(sum num_fg, 1), :148-154)
+ * Floating point: fp32 sums in a fixed (deterministic) order that differs from ATen's — within 1e-5 relative.
+ * Workspace: plyolo_yolox_loss_workspace_bytes(B, A); 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t plyolo_yolox_loss_workspace_bytes(int B, int A);
+int plyolo_yolox_loss_f32(const float *preds, const float *labels, const uint8_t *fg_mask,
+                          const int32_t *matched_gt, const float *matched_iou, int B, int A, int C, int Lmax,
+                          float *sums, void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+
+/* Backward of the three sums straight into the head maps: d(sums . grad_sums) / d(head map l), chained through
+ * the training-mode decode (yolox_loss.py:217-219) — what autograd computes for
+ * YOLOXLoss.__call__(inputs, labels)["loss"].backward() between the loss dict and the head outputs.
+ *   grad_sums      [3] fp32 device: upstream gradient of the three sums (5/N, 1/N, 1/N for the reference's loss)
+ *   host_grad_lvl  host array of n_levels device pointers, level l = [B, 5+C, hs[l], ws[l]], fully overwritten */
+int plyolo_yolox_loss_backward_f32(const float *preds, const float *labels, const uint8_t *fg_mask,
+                                   const int32_t *matched_gt, const float *matched_iou, int B, int C, int Lmax,
+                                   const float *grad_sums, float *const *host_grad_lvl, const int *hs,
+                                   const int *ws, const int *strides, int n_levels, plyolo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

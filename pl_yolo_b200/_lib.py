@@ -44,6 +44,13 @@ def _declare(lib):
     lib.plyolo_format_dets_f32.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
     lib.plyolo_bboxes_iou_f32.restype = c_int
     lib.plyolo_bboxes_iou_f32.argtypes = [vp, c_int, vp, c_int, c_int, vp, vp]
+    lib.plyolo_yolox_loss_workspace_bytes.restype = c_size_t
+    lib.plyolo_yolox_loss_workspace_bytes.argtypes = [c_int, c_int]
+    lib.plyolo_yolox_loss_f32.restype = c_int
+    lib.plyolo_yolox_loss_f32.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_size_t, vp]
+    lib.plyolo_yolox_loss_backward_f32.restype = c_int
+    lib.plyolo_yolox_loss_backward_f32.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp, POINTER(c_void_p), ip, ip,
+                                                   ip, c_int, vp]
 
 
 def lib() -> ctypes.CDLL:

@@ -212,6 +212,73 @@ def _(preds, labels, hw, strides):
             preds.new_empty((B, A)), preds.new_empty((B,), dtype=torch.int32), preds.new_empty((B,), dtype=torch.int32))
 
 
+# ------------------------------------------------------------------------------------------ loss tail (N2)
+def _loss_inputs(preds, labels, fg_mask, matched_gt, matched_iou):
+    p = _check_cuda_f32(preds, "preds")
+    lab = _check_cuda_f32(labels, "labels")
+    mi = _check_cuda_f32(matched_iou, "matched_iou")
+    if p.dim() != 3 or lab.dim() != 3 or lab.shape[2] != 5 or lab.shape[0] != p.shape[0]:
+        raise ValueError("preds must be [B,A,5+C] and labels [B,Lmax,5]")
+    B, A, _ = p.shape
+    fg = fg_mask.contiguous()
+    fg = fg.view(torch.uint8) if fg.dtype == torch.bool else fg
+    if fg.dtype != torch.uint8 or matched_gt.dtype != torch.int32:
+        raise TypeError("fg_mask must be bool / uint8 and matched_gt int32 (the outputs of simota_assign)")
+    mg = matched_gt.contiguous()
+    for t, n in ((fg, "fg_mask"), (mg, "matched_gt"), (mi, "matched_iou")):
+        if not t.is_cuda or tuple(t.shape) != (B, A):
+            raise ValueError("%s must be a CUDA tensor of shape [B, A]" % n)
+    return p, lab, fg, mg, mi
+
+
+def yolox_loss_sums_raw(preds: torch.Tensor, labels: torch.Tensor, fg_mask: torch.Tensor, matched_gt: torch.Tensor,
+                        matched_iou: torch.Tensor) -> torch.Tensor:
+    """Loss tail of YOLOXLoss (yolox_loss.py:121-154, use_l1=False): -> [3] = (sum GIoU loss over the foreground
+    anchors, sum objectness BCE over all anchors, sum class BCE over the foreground anchors)."""
+    p, lab, fg, mg, mi = _loss_inputs(preds, labels, fg_mask, matched_gt, matched_iou)
+    B, A, ch = p.shape
+    dev = p.device
+    sums = torch.empty((3,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _workspace("loss", L.plyolo_yolox_loss_workspace_bytes(B, A), dev)
+        rc = L.plyolo_yolox_loss_f32(p.data_ptr(), lab.data_ptr(), fg.data_ptr(), mg.data_ptr(), mi.data_ptr(), B, A,
+                                     ch - 5, lab.shape[1], sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_yolox_loss_f32")
+    return sums
+
+
+def yolox_loss_backward_raw(preds: torch.Tensor, labels: torch.Tensor, fg_mask: torch.Tensor, matched_gt: torch.Tensor,
+                            matched_iou: torch.Tensor, grad_sums: torch.Tensor, hw: List[int],
+                            strides: List[int]) -> List[torch.Tensor]:
+    """d(sums . grad_sums) / d(head maps), chained through the training-mode decode: one [B,5+C,H,W] tensor per level."""
+    p, lab, fg, mg, mi = _loss_inputs(preds, labels, fg_mask, matched_gt, matched_iou)
+    g = _check_cuda_f32(grad_sums, "grad_sums")
+    if g.numel() != 3:
+        raise ValueError("grad_sums must have 3 elements")
+    B, A, ch = p.shape
+    hs, ws_ = list(hw[0::2]), list(hw[1::2])
+    if sum(h * w for h, w in zip(hs, ws_)) != A:
+        raise ValueError("the level shapes do not add up to A")
+    dev = p.device
+    grads = [torch.empty((B, ch, h, w), dtype=torch.float32, device=dev) for h, w in zip(hs, ws_)]
+    with torch.cuda.device(dev):
+        rc = _lib.lib().plyolo_yolox_loss_backward_f32(
+            p.data_ptr(), lab.data_ptr(), fg.data_ptr(), mg.data_ptr(), mi.data_ptr(), B, ch - 5, lab.shape[1],
+            g.data_ptr(), _lib.ptr_array([t.data_ptr() for t in grads]), _lib.int_array(hs), _lib.int_array(ws_),
+            _lib.int_array(strides), len(hs), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_yolox_loss_backward_f32")
+    return grads
+
+
+yolox_loss_sums = torch.library.custom_op("plyolo::yolox_loss_sums", yolox_loss_sums_raw, mutates_args=())
+
+
+@yolox_loss_sums.register_fake
+def _(preds, labels, fg_mask, matched_gt, matched_iou):
+    return preds.new_empty((3,))
+
+
 # ------------------------------------------------------------------------------------- format_dets
 def format_dets_raw(dets: torch.Tensor, counts: torch.Tensor, inv_scales: torch.Tensor) -> torch.Tensor:
     """Device part of format_outputs: [B,max_det,6] + counts + per-image (float)(1/scale) -> [B,max_det,8] rows

@@ -81,6 +81,63 @@ def test_training_step_backward_runs():
     assert all(h.grad is not None and torch.isfinite(h.grad).all() for h in heads)
 
 
+def _grad_close(a, b, what):
+    scale = float(b.abs().max())
+    err = float((a - b).abs().max())
+    assert err <= 1e-5 * scale + 1e-12, "%s: max |diff| %.3e vs max |ref| %.3e" % (what, err, scale)
+
+
+@pytest.mark.parametrize("B,size,lmax,seed", [(2, 160, 10, 30), (4, 320, 40, 31), (8, 640, 120, 32)])
+def test_fused_loss_tail_matches_torch_tail(B, size, lmax, seed):
+    """N2: the fused loss tail (forward sums + backward straight into the head maps) against the batched torch
+    code of the same shim (itself pinned to the real reference's loss dict by the golden fixtures): values within
+    1e-5 relative, head-map gradients within 1e-5 of the largest gradient of the level."""
+    heads = synth.make_heads(B, size, 80, seed)
+    labels = cu(synth.make_labels(B, size, lmax, 80, seed + 100))
+    a = [cu(h).requires_grad_(True) for h in heads]
+    b = [cu(h).requires_grad_(True) for h in heads]
+    fused = YOLOXLoss(80, STRIDES)(a, labels)
+    plain = YOLOXLoss(80, STRIDES, fused_loss=False)(b, labels)
+    for k in ("loss", "loss_iou", "loss_obj", "loss_cls", "proportion"):
+        assert float(fused[k]) == pytest.approx(float(plain[k]), rel=1e-5, abs=1e-7), k
+    assert fused["loss_l1"] == 0.0
+    fused["loss"].backward()
+    plain["loss"].backward()
+    for l, (x, y) in enumerate(zip(a, b)):
+        assert x.grad.shape == y.grad.shape
+        _grad_close(x.grad, y.grad, "level %d" % l)
+        for lo, hi, nm in ((0, 4, "box"), (4, 5, "obj"), (5, 85, "cls")):
+            if float(y.grad[:, lo:hi].abs().max()) > 0:
+                _grad_close(x.grad[:, lo:hi], y.grad[:, lo:hi], "level %d %s" % (l, nm))
+
+
+def test_fused_loss_component_gradients_and_edges():
+    """Each of the three sums separately (different upstream gradients), an image without GTs, and the C-ABI errors."""
+    B, size = 3, 160
+    heads = synth.make_heads(B, size, 80, 40)
+    lab = synth.make_labels(B, size, 12, 80, 41)
+    lab[1] = 0  # no GT in image 1: every anchor background, only the objectness term
+    labels = cu(lab)
+    for w in ([1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.3, 2.0, 0.7]):
+        a = [cu(h).requires_grad_(True) for h in heads]
+        b = [cu(h).requires_grad_(True) for h in heads]
+        f = YOLOXLoss(80, STRIDES)(a, labels)
+        g = YOLOXLoss(80, STRIDES, fused_loss=False)(b, labels)
+        (w[0] * f["loss_iou"] + w[1] * f["loss_obj"] + w[2] * f["loss_cls"]).backward()
+        (w[0] * g["loss_iou"] + w[1] * g["loss_obj"] + w[2] * g["loss_cls"]).backward()
+        for l, (x, y) in enumerate(zip(a, b)):
+            _grad_close(x.grad, y.grad, "weights %s level %d" % (w, l))
+    preds, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    fg, mg, mi, nfg, ngt = ops.simota_assign_raw(preds, labels, [20, 20, 10, 10, 5, 5], STRIDES)
+    sums = ops.yolox_loss_sums_raw(preds, labels, fg, mg, mi)
+    assert sums.shape == (3,) and torch.isfinite(sums).all()
+    assert torch.equal(sums, ops.yolox_loss_sums_raw(preds, labels, fg, mg, mi)), "the sums must be deterministic"
+    with pytest.raises(Exception):
+        ops.yolox_loss_sums_raw(preds.cpu(), labels, fg, mg, mi)
+    with pytest.raises(Exception):
+        ops.yolox_loss_backward_raw(preds, labels, fg, mg, mi, sums, [20, 20, 10, 10], STRIDES[:2])
+
+
 def test_bboxes_iou_guard():
     with pytest.raises(IndexError):
         bboxes_iou(torch.zeros(2, 5, device=DEV), torch.zeros(3, 4, device=DEV))
