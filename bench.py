@@ -363,6 +363,53 @@ def main():
     sim_bytes = BYTES_SIMOTA + 20 * gt_mean
     sim_achieved = BATCH * sim_bytes / (sms * 1e-3 / K) / 1e9
 
+    # ------------------------------------------------------------------ training path (N2): decode -> SimOTA -> loss tail
+    # forward + backward to the head maps, kernels only (what YOLOXLoss(train)(heads, labels)["loss"].backward() runs)
+    train = None
+    try:
+        gsum = torch.tensor([5.0 / 3000, 1.0 / 3000, 1.0 / 3000], device=dev)
+
+        def train_eager(s):
+            pr, _ = ops.decode_raw(heads[s], STRIDES, False)
+            fg_, mg_, mi_, _, _ = ops.simota_assign_raw(pr, labels[s], hw, STRIDES)
+            sums_ = ops.yolox_loss_sums_raw(pr, labels[s], fg_, mg_, mi_)
+            return sums_, ops.yolox_loss_backward_raw(pr, labels[s], fg_, mg_, mi_, gsum, hw, STRIDES)
+
+        tr_graphs, tr_lpg = None, 0
+        if graphs is not None:
+            with torch.cuda.stream(stream):
+                for s in range(N_SETS):
+                    train_eager(s)
+                torch.cuda.synchronize(dev)
+                tr_graphs, tr_keep = [], []
+                for s in range(N_SETS):
+                    g = torch.cuda.CUDAGraph()
+                    l0 = _lib.launch_count()
+                    with torch.cuda.graph(g, stream=stream):
+                        tr_keep.append(train_eager(s))
+                    tr_lpg = _lib.launch_count() - l0
+                    tr_graphs.append(g)
+
+        def train_step(i):
+            if tr_graphs is not None:
+                tr_graphs[i % N_SETS].replay()
+            else:
+                train_eager(i % N_SETS)
+
+        tms, _, tl = timed(train_step)
+        if tr_graphs is not None:
+            tl = tr_lpg * K
+        # compulsory traffic: head maps read, preds written + read back by the assignment / loss, head-map gradients written
+        tbytes = BATCH * (A * 85 * 4 * 3 + A * 9)
+        train = {"value": world * BATCH * K / (tms * 1e-3), "unit": "img/s", "ms_per_step": tms / K, "gpu_launches": int(tl),
+                 "workload": "YOLOX loss training path batch 32 (decode + SimOTA + loss tail forward, backward into the head maps) "
+                             "[SURVEY 8f N2]",
+                 "roofline": {"bound": "hbm", "achieved": tbytes / (tms * 1e-3 / K) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": tbytes / (tms * 1e-3 / K) / 1e9 / peak, "algorithmic_bytes_per_step": tbytes}}
+    except Exception as e:  # noqa: BLE001
+        train = {"unavailable": repr(e)[:200]}
+        torch.cuda.synchronize(dev)
+
     # ------------------------------------------------------------------ end to end through the public API, host buffers
     pinned = [[torch.from_numpy(h).pin_memory() for h in hs] for hs in heads_np]
     stage = [[torch.empty_like(h, device=dev) for h in pinned[0]] for _ in range(2)]
@@ -438,6 +485,8 @@ def main():
                                     "note": "latency/issue-bound: the assignment touches ~25 MB of the 94 MB algorithmic bytes"},
                        "clocks": sclocks},
         }
+        if train is not None:
+            line["train_path"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
