@@ -251,6 +251,23 @@ def simota_cases():
     gen_simota("simota_edges", 8, S, 29, 0, 12, labels=L)
 
 
+# ------------------------------------------------------------------------------- loss tail gradients (N2)
+def gen_lossgrad(name, B, size, seed_h, seed_l, max_labels, C=80):
+    """The real reference's training loss and its autograd gradients with respect to the head outputs
+    (YOLOXLoss.__call__ in training mode, yolox_loss.py:20-173; decode mutates its inputs in place, quirk Q1, so the
+    leaves are cloned first)."""
+    heads = synth.make_heads(B, size, C, seed_h)
+    labels = synth.make_labels(B, size, max_labels, C, seed_l)
+    leaves = [T(h).clone().requires_grad_(True) for h in heads]
+    out = YOLOXLoss(C, STRIDES)([x.clone() for x in leaves], T(labels))
+    out["loss"].backward()
+    losses = {k: float(v) for k, v in out.items()}
+    save(name, dict(kind="lossgrad", B=B, size=size, C=C, strides=STRIDES, seed_heads=seed_h,
+                    labels=dict(gen="synth", seed=seed_l, max_labels=max_labels, min_gt=1, max_gt=None),
+                    sha_heads=synth.digest(*heads), sha_labels=synth.digest(labels), losses=losses),
+         **{"grad%d" % l: x.grad.numpy() for l, x in enumerate(leaves)})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["decode", "post", "simota"]
     if "decode" in which:
@@ -261,3 +278,6 @@ if __name__ == "__main__":
         post_cases()
     if "simota" in which:
         simota_cases()
+    if "lossgrad" in which:  # added with N2; not part of the default set so the older fixtures stay byte-identical
+        gen_lossgrad("lossgrad_160_b2", 2, 160, 51, 52, 12)
+        gen_lossgrad("lossgrad_320_b2", 2, 320, 53, 54, 40)

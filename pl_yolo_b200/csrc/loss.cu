@@ -113,17 +113,33 @@ __global__ void __launch_bounds__(kLossThreads) yolox_loss_fwd_kernel(const Loss
     }
     // class terms of the warp's foreground anchors, lanes over classes (:154; target one_hot(class) * IoU, :123-125)
     unsigned m = __ballot_sync(0xffffffffu, fg);
-    while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const float *rj = p.preds + ((size_t)b * p.A + (a - lane + j)) * p.ch + 5;
-        const int gcj = __shfl_sync(0xffffffffu, gc, j);
-        const float tj = __shfl_sync(0xffffffffu, tiou, j);
-        float v = 0.f;
-        for (int c = lane; c < p.C; c += 32) v += bce_logits(__ldg(rj + c), c == gcj ? tj : 0.f);
+    while (m) {  // four foreground anchors per trip: their rows are in flight together
+        constexpr int U = 4, NK = (PLYOLO_MAX_CLASSES + 31) / 32;
+        int jj[U];
+        float x[U][NK];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_cls += v;
+        for (int u = 0; u < U; ++u) {
+            jj[u] = m ? __ffs(m) - 1 : -1;
+            m &= m - 1;  // 0 stays 0
+            const float *rj = p.preds + ((size_t)b * p.A + (a - lane + max(jj[u], 0))) * p.ch + 5;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) x[u][k] = (jj[u] >= 0 && lane + 32 * k < p.C) ? __ldg(rj + lane + 32 * k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (jj[u] < 0) break;  // warp-uniform
+            const int gcj = __shfl_sync(0xffffffffu, gc, jj[u]);
+            const float tj = __shfl_sync(0xffffffffu, tiou, jj[u]);
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const int c = lane + 32 * k;
+                if (c < p.C) v += bce_logits(x[u][k], c == gcj ? tj : 0.f);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_cls += v;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -161,6 +177,7 @@ struct LossBwdParams {
     LossParams f;
     Levels lv;            // ptr[l] = gradient of head map l (written)
     const float *gscale;  // [3] device: upstream gradient of (sum giou, sum obj, sum cls)
+    int vec_ok;           // 128-bit stores are aligned
 };
 
 __global__ void __launch_bounds__(kLossThreads) yolox_loss_bwd_kernel(const LossBwdParams p) {
@@ -175,7 +192,7 @@ __global__ void __launch_bounds__(kLossThreads) yolox_loss_bwd_kernel(const Loss
     const int cnt = min(kLossTile, hw - a0);
     const int ch = p.f.ch, C = p.f.C;
     const float g_iou = p.gscale[0], g_obj = p.gscale[1], g_cls = p.gscale[2];
-    for (int i = tid; i < ch * kLossTile; i += kLossThreads) gt[i] = 0.f;
+    for (int i = tid; i < ch * kLossTile / 4; i += kLossThreads) reinterpret_cast<float4 *>(gt)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     // threads [0, 128): one anchor each — objectness of every anchor, box terms of the foreground ones;
     // then every warp handles the class rows of its own foreground anchors, lanes over classes
@@ -218,9 +235,16 @@ __global__ void __launch_bounds__(kLossThreads) yolox_loss_bwd_kernel(const Loss
     __syncthreads();
     // channel-planar store: row c of the tile = cnt consecutive cells of plane c of the head-map gradient
     float *dst = const_cast<float *>(p.lv.ptr[l]) + (size_t)b * ch * hw + a0;
-    for (int i = tid; i < ch * kLossTile; i += kLossThreads) {
-        const int c = i / kLossTile, x = i - c * kLossTile;
-        if (x < cnt) dst[(size_t)c * hw + x] = gt[i];
+    if (p.vec_ok) {  // every level size a multiple of 4, 16-byte aligned maps: 128-bit stores
+        for (int i = tid; i < ch * (kLossTile / 4); i += kLossThreads) {
+            const int c = i / (kLossTile / 4), x4 = i - c * (kLossTile / 4);
+            if (x4 * 4 < cnt) reinterpret_cast<float4 *>(dst + (size_t)c * hw)[x4] = reinterpret_cast<const float4 *>(gt + c * kLossTile)[x4];
+        }
+    } else {
+        for (int i = tid; i < ch * kLossTile; i += kLossThreads) {
+            const int c = i / kLossTile, x = i - c * kLossTile;
+            if (x < cnt) dst[(size_t)c * hw + x] = gt[i];
+        }
     }
 }
 
@@ -286,6 +310,9 @@ extern "C" int plyolo_yolox_loss_backward_f32(const float *preds, const float *l
     p.f.B = B; p.f.A = p.lv.A; p.f.C = C; p.f.ch = 5 + C; p.f.Lmax = Lmax;
     p.f.partial = nullptr; p.f.sums = nullptr;
     p.gscale = grad_sums;
+    bool vec = true;
+    for (int l = 0; l < p.lv.n; ++l) vec = vec && ((uintptr_t)p.lv.ptr[l] & 15) == 0 && (p.lv.hw[l] & 3) == 0;
+    p.vec_ok = vec ? 1 : 0;
     const size_t smem = (size_t)kLossTile * p.f.ch * sizeof(float);
     static thread_local bool attr_done = false;
     if (!attr_done) {

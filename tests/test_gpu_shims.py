@@ -111,6 +111,21 @@ def test_fused_loss_tail_matches_torch_tail(B, size, lmax, seed):
                 _grad_close(x.grad[:, lo:hi], y.grad[:, lo:hi], "level %d %s" % (l, nm))
 
 
+@pytest.mark.parametrize("name", names("lossgrad"))
+def test_fused_loss_vs_real_reference_gradients(name):
+    """N2 against the REAL reference: loss dict and autograd gradients of the head outputs recorded from
+    /root/reference's YOLOXLoss on CPU (oracle/gen_golden.py lossgrad)."""
+    meta, g = load(name)
+    heads = [cu(h).requires_grad_(True) for h in heads_of(meta)]
+    labels = cu(labels_of(meta, g))
+    out = YOLOXLoss(80, STRIDES)(heads, labels)
+    for k, v in meta["losses"].items():
+        assert float(out[k]) == pytest.approx(v, rel=2e-5, abs=1e-6), k
+    out["loss"].backward()
+    for l, h in enumerate(heads):
+        _grad_close(h.grad, cu(g["grad%d" % l]), "%s level %d" % (name, l))
+
+
 def test_fused_loss_component_gradients_and_edges():
     """Each of the three sums separately (different upstream gradients), an image without GTs, and the C-ABI errors."""
     B, size = 3, 160
