@@ -384,8 +384,14 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
     }
     __syncthreads();
     // the CTA's seq-th tile: adjacent tiles come in pairs, so that one CTA asks for 1 KB of every channel plane
-    // back to back (DRAM page locality)
-    auto tile_of = [&](const int seq) { return 2 * ((int)blockIdx.x + (seq >> 1) * (int)gridDim.x) + (seq & 1); };
+    // back to back
+    // (DRAM page locality); the tiles left over after the last complete round of pairs are dealt singly, so that
+    // no CTA gets more than one tile above the average (2144 tiles on 148 SMs: 15 instead of 16)
+    const int grid = (int)gridDim.x, full = ((total + 1) / 2) / grid;
+    auto tile_of = [&](const int seq) {
+        if (seq < 2 * full) return 2 * ((int)blockIdx.x + (seq >> 1) * grid) + (seq & 1);
+        return 2 * full * grid + (seq - 2 * full) * grid + (int)blockIdx.x;
+    };
     if (warp < kProducers) {
         // ---- producers
         if ((!FUSED || use_tmap) && warp > 0) return;  // one request per tile: one warp is plenty
