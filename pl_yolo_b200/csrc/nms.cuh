@@ -385,55 +385,6 @@ __device__ __forceinline__ void warp_class_nms(const unsigned long long *keys, c
     }
 }
 
-// Same sweep over a segment whose (offset) boxes already sit in box_s[s, e) in score order; the kept boxes
-// are compacted in place to the head of the segment (the write position never passes the chunk being
-// processed, whose boxes are in registers by then).
-__device__ __forceinline__ void warp_class_nms_inplace(float4 *box_s, unsigned *keep_bits, const int s, const int e,
-                                                       const int max_det, const int flavor, const float thr_f,
-                                                       const double thr_d) {
-    const int lane = threadIdx.x & 31;
-    int K = 0;
-    for (int c0 = s; c0 < e && K < max_det; c0 += 32) {
-        const int i = c0 + lane;
-        const bool valid = i < e;
-        const float4 bx = valid ? box_s[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        bool dead = !valid;
-        for (int k = 0; k < K; k += 4) {
-            if (__all_sync(0xffffffffu, dead)) break;  // dense clusters die against the first keeps
-            // 4 independent tests per trip (entries past K are later boxes of the buffer: masked)
-            const float4 k0 = box_s[s + k], k1 = box_s[s + k + 1], k2 = box_s[s + k + 2], k3 = box_s[s + k + 3];
-            const bool s0 = suppresses(k0, bx, flavor, thr_f, thr_d);
-            const bool s1 = k + 1 < K && suppresses(k1, bx, flavor, thr_f, thr_d);
-            const bool s2 = k + 2 < K && suppresses(k2, bx, flavor, thr_f, thr_d);
-            const bool s3 = k + 3 < K && suppresses(k3, bx, flavor, thr_f, thr_d);
-            dead = dead || s0 || s1 || s2 || s3;
-        }
-        unsigned alive = __ballot_sync(0xffffffffu, !dead);
-        unsigned keepm = 0u;
-        int room = max_det - K;
-        while (alive && room > 0) {
-            const int j = __ffs(alive) - 1;  // lowest surviving lane == best remaining score: kept
-            keepm |= 1u << j;
-            alive &= ~(1u << j);
-            --room;
-            if (!alive) break;
-            const float4 jb = make_float4(__shfl_sync(0xffffffffu, bx.x, j), __shfl_sync(0xffffffffu, bx.y, j),
-                                          __shfl_sync(0xffffffffu, bx.z, j), __shfl_sync(0xffffffffu, bx.w, j));
-            const bool sup = ((alive >> lane) & 1u) && suppresses(jb, bx, flavor, thr_f, thr_d);
-            alive &= ~__ballot_sync(0xffffffffu, sup);
-        }
-        __syncwarp();
-        if ((keepm >> lane) & 1u) box_s[s + K + __popc(keepm & ((1u << lane) - 1u))] = bx;
-        if (lane == 0 && keepm) {
-            const int w = c0 >> 5, sh = c0 & 31;
-            atomicOr(&keep_bits[w], keepm << sh);
-            if (sh && (keepm >> (32 - sh))) atomicOr(&keep_bits[w + 1], keepm >> (32 - sh));
-        }
-        K += __popc(keepm);
-        __syncwarp();
-    }
-}
-
 // writes the image's output rows (postprocess.py:43-46): score order, zero padded to max_det
 template <typename SlotOf>
 __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, const size_t slot0, const int nkept,

@@ -29,27 +29,16 @@ constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged
 constexpr int kImgCtr = 8;      // ints per image in the counter block (zeroed before every call)
 
 constexpr size_t kNmsSmemLimit = 190 * 1024;  // dynamic shared memory of the NMS kernels (33 KB are static)
-constexpr int kRecCap = 1024;   // >= max_det: a group contributes at most max_det rows to the image's output
-
-struct __align__(16) KeptRec {  // one kept box as the merge needs it
-    unsigned long long key;     // ~ordered(score) << 25 | slot: the global order
-    float score;
-    int meta;                   // anchor | class << 24
-    float4 box;
-};
-
 struct CandWs {
     int *tile_count;    // [B, NT]
     float4 *box;        // [B, NT*128]  original (un-offset) corners
     float *score;       // [B, NT*128]
     int *meta;          // [B, NT*128]  anchor | class << 24
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
-    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | #done CTAs | fallback
+    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | (unused)
     unsigned long long *gkey;     // [B, kGroups, NT*128]  class << 57 | ~ordered(score) << 25 | slot
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
-    KeptRec *krec;                // [B, kGroups, kRecCap] first kept boxes of every group, global order
-    int *kcount;                  // [B, kGroups]
 };
 
 struct ScoreParams {
@@ -473,8 +462,6 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t o_gkey = take(slots * kGroups * sizeof(unsigned long long));
     size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
     size_t o_xbox = take((size_t)B * kMaxCross * sizeof(float4));
-    size_t o_kept = take((size_t)B * kGroups * kRecCap * sizeof(KeptRec));
-    size_t o_kcnt = take((size_t)B * kGroups * sizeof(int));
     if (ws) {
         ws->ctr = reinterpret_cast<int *>(base + o_ctr);
         ws->tile_count = reinterpret_cast<int *>(base + o_cnt);
@@ -484,8 +471,6 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
         ws->gkey = reinterpret_cast<unsigned long long *>(base + o_gkey);
         ws->xkey = reinterpret_cast<unsigned long long *>(base + o_xkey);
         ws->xbox = reinterpret_cast<float4 *>(base + o_xbox);
-        ws->krec = reinterpret_cast<KeptRec *>(base + o_kept);
-        ws->kcount = reinterpret_cast<int *>(base + o_kcnt);
     }
     return off;
 }

@@ -763,7 +763,6 @@ struct MatchShared {
     float pos[kGtPerCta][kMaxBoth];    // positive BCE leaf of the pair (exact)
     float so[kGtPerCta][kMaxBoth];     // 1 / sigmoid(obj) of the pair's anchor
     float lso[kGtPerCta][kMaxBoth];    // log2 of it
-    float top[kMatchWarps][10];
     float terms[kMatchWarps][96];
     int conf[kMaxConf];
     int k[kGtPerCta], nb[kGtPerCta], gcls[kGtPerCta], gidx[kGtPerCta];
