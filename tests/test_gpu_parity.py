@@ -500,6 +500,23 @@ def test_simota_iou_sweep_routes():
     assert_simota_equal(run_simota(preds, lab, size), o, "same-lane top-10 (fallback)")
 
 
+def test_simota_more_than_one_sweep_chunk():
+    """More than 1024 candidate groups (a GT covering a 1312^2 image: every one of the 35301 anchors is a candidate):
+    the IoU sweep lists the groups in several passes."""
+    size = 1312
+    heads = synth.make_heads(1, size, 80, 71, objects_per_image=20)
+    dec, _ = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    preds = dec.cpu().numpy()
+    lab = np.zeros((1, 6, 5), np.float32)
+    lab[0, 0] = [3, 656, 656, 1308, 1308]
+    lab[0, 1] = [7, 300, 400, 200, 150]
+    lab[0, 2] = [9, 900, 1000, 50, 60]
+    lab[0, 3] = [11, 1200, 200, 600, 300]
+    o = oracle.simota(preds, lab, synth.level_shapes(size), STRIDES)
+    assert int(o["n_cand"][0]) > 1024 * 32, "test construction: needs more than 1024 candidate groups"
+    assert_simota_equal(run_simota(preds, lab, size), o, "oracle, multi-chunk sweep")
+
+
 def test_simota_small_class_counts():
     rng = np.random.default_rng(4)
     for C, shapes, strides in [(1, [(8, 8), (4, 4)], [8, 16]), (20, [(16, 16), (8, 8), (4, 4)], [8, 16, 32]), (33, [(16, 16)], [8])]:
