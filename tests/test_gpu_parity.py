@@ -168,6 +168,33 @@ def test_fused_decode_postprocess(B, size, seed, mode):
     assert (np.abs(o["counts"] - rc) <= 2).all()
 
 
+@pytest.mark.parametrize("C", [1, 3, 20, 33, 91])
+def test_fused_other_class_counts(C):
+    """Class counts that are not a multiple of the score kernel's 16-class chunks (VOC has 20): fused route ==
+    decode -> postprocess == the reference op chain on CUDA."""
+    heads = [cu(h) for h in synth.make_heads(3, 320, C, 80 + C)]
+    preds, _ = ops.decode_raw(heads, STRIDES, True)
+    d1, c1, k1 = ops.postprocess_raw(preds, 0.01, 0.65, False, 10000, 300, 0)
+    d2, c2, k2 = ops.decode_postprocess_raw(heads, STRIDES, 0.01, 0.65, False, 10000, 300, 0)
+    assert torch.equal(c1, c2) and torch.equal(k1, k2) and torch.equal(d1, d2), "fused path differs from decode->postprocess"
+    rd, rc = replay_dets(R.decode(heads, STRIDES, True)[0], 0.01, 0.65, False)
+    assert np.array_equal(c2.cpu().numpy(), rc)
+    assert np.array_equal(d2.cpu().numpy(), rd), "differs from the reference op chain on CUDA"
+    assert int(c2.sum()) > 0
+
+
+def test_postprocess_large_max_det():
+    """max_det above the cluster merge's shared-memory budget (> 800): every image takes the single-CTA path."""
+    rng = np.random.default_rng(13)
+    n = 3000
+    xy = rng.uniform(0, 3000, (n, 2))
+    wh = rng.uniform(4, 60, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    p = _raw_preds(boxes, rng.uniform(0.05, 1, n).astype(np.float32), rng.integers(0, 80, n), A=n)
+    _check_post_vs_oracle(p, max_det=1000, flavors=(0,))
+    _check_post_vs_oracle(p, max_det=800, flavors=(0,))
+
+
 def test_fused_argmax_saturation_and_near_ties():
     """Argmax is taken over the sigmoid VALUES (postprocess.py:18): saturated logits tie at 1.0 and the
     first class wins, logits a few ulp apart may round to the same or even an inverted sigmoid.  The fused kernel
