@@ -99,7 +99,7 @@ def test_fused_loss_tail_matches_torch_tail(B, size, lmax, seed):
     fused = YOLOXLoss(80, STRIDES)(a, labels)
     plain = YOLOXLoss(80, STRIDES, fused_loss=False)(b, labels)
     for k in ("loss", "loss_iou", "loss_obj", "loss_cls", "proportion"):
-        assert float(fused[k]) == pytest.approx(float(plain[k]), rel=1e-5, abs=1e-7), k
+        assert float(torch.as_tensor(fused[k]).detach()) == pytest.approx(float(torch.as_tensor(plain[k]).detach()), rel=1e-5, abs=1e-7), k
     assert fused["loss_l1"] == 0.0
     fused["loss"].backward()
     plain["loss"].backward()
@@ -124,6 +124,23 @@ def test_fused_loss_vs_real_reference_gradients(name):
     out["loss"].backward()
     for l, h in enumerate(heads):
         _grad_close(h.grad, cu(g["grad%d" % l]), "%s level %d" % (name, l))
+
+
+@pytest.mark.parametrize("C", [1, 20, 91])
+def test_fused_loss_other_class_counts(C):
+    """N2 with class counts that are not a multiple of the warp width (VOC has 20)."""
+    heads = synth.make_heads(3, 320, C, 90 + C)
+    labels = cu(synth.make_labels(3, 320, 20, C, 190 + C))
+    a = [cu(h).requires_grad_(True) for h in heads]
+    b = [cu(h).requires_grad_(True) for h in heads]
+    fused = YOLOXLoss(C, STRIDES)(a, labels)
+    plain = YOLOXLoss(C, STRIDES, fused_loss=False)(b, labels)
+    for k in ("loss", "loss_iou", "loss_obj", "loss_cls", "proportion"):
+        assert float(torch.as_tensor(fused[k]).detach()) == pytest.approx(float(torch.as_tensor(plain[k]).detach()), rel=1e-5, abs=1e-7), k
+    fused["loss"].backward()
+    plain["loss"].backward()
+    for l, (x, y) in enumerate(zip(a, b)):
+        _grad_close(x.grad, y.grad, "C=%d level %d" % (C, l))
 
 
 def test_fused_loss_component_gradients_and_edges():
