@@ -8,7 +8,8 @@ B = 32
 heads = [torch.from_numpy(h).cuda() for h in synth.make_heads(B, 640, 80, seed=0)]
 L = _lib.lib()
 L.plyolo_debug_score_profile.argtypes = [ctypes.c_void_p]
-prof = torch.zeros((148, 3, 8), dtype=torch.int64, device="cuda")
+KC = 4  # kConsumers of postprocess.cu (the kernel indexes [blockIdx.x][kConsumers][8])
+prof = torch.zeros((148, KC, 8), dtype=torch.int64, device="cuda")
 for _ in range(3):
     ops.decode_postprocess_raw(heads, [8, 16, 32], 0.01, 0.65, False, 10000, 300, 0)
 L.plyolo_debug_score_profile(prof.data_ptr())
