@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint8, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -14,6 +15,7 @@ FLAVOR_CUDA, NMS_RULE_CPU, IOU_NOFMA, THR_F64, FLAVOR_CPU = 0, 1, 2, 4, 7
 MAX_LEVELS = 8
 
 _lib = None
+_lock = threading.Lock()
 
 
 class PlyoloError(RuntimeError):
@@ -54,19 +56,29 @@ def _declare(lib):
 
 
 def lib() -> ctypes.CDLL:
-    """Loads (building first if the sources are newer and nvcc is present) the in-tree library."""
+    """Loads the in-tree library; builds it first when it is missing or older than its sources and nvcc is present
+    (a stale library with no compiler around — the GPU box always has one — is loaded as it is).  PLYOLO_LIB points
+    at another build of the same ABI (kernel variants during tuning)."""
     global _lib
-    if _lib is None:
-        if not os.path.exists(SO_PATH):
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = os.environ.get("PLYOLO_LIB") or SO_PATH
+        if path == SO_PATH:
+            from . import build as _build
             try:
-                from . import build as _build
-                _build.build()
+                if _build.needs_build():
+                    _build.build()
             except Exception as e:  # noqa: BLE001
-                raise PlyoloError(
-                    "libplyolo.so is missing and could not be built (%s). Run `python -m pl_yolo_b200.build` "
-                    "(needs nvcc); there is no CPU or PyTorch fallback for these ops." % (e,)) from e
-        _lib = ctypes.CDLL(SO_PATH)
-        _declare(_lib)
+                if not os.path.exists(SO_PATH):
+                    raise PlyoloError(
+                        "libplyolo.so is missing and could not be built (%s). Run `python -m pl_yolo_b200.build` "
+                        "(needs nvcc); there is no CPU or PyTorch fallback for these ops." % (e,)) from e
+        handle = ctypes.CDLL(path)
+        _declare(handle)
+        _lib = handle
     return _lib
 
 

@@ -103,21 +103,10 @@ __host__ __device__ inline size_t nms_smem_bytes(const int sort_cap, const int f
            (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned);
 }
 
-// nms_group_kernel: the single-CTA layout (fallback), its own fast layout, or the merge's record lists
-// nms_group_kernel: the single-CTA layout (fallback) or its own fast layout followed by the merge's key lists
-__host__ __device__ inline size_t nms_group_merge_offset(const int fast_cap) {
-    return ((size_t)fast_cap * 40 + (size_t)((fast_cap >> 5) + 1) * sizeof(unsigned) + 15) & ~(size_t)15;
-}
-__host__ __device__ inline size_t nms_group_smem_bytes(const int sort_cap, const int fast_cap, const int max_det, const int NT) {
-    size_t m = nms_smem_bytes(sort_cap, fast_cap, max_det, NT);
-    const size_t fast_b = nms_group_merge_offset(fast_cap) + ((size_t)kGroups * max_det + 64) * sizeof(unsigned long long);
-    if (fast_b > m) m = fast_b;
-    return (m + 15) & ~(size_t)15;
-}
-
 struct NmsParams {
     int B, NT, max_nms, max_det, flavor, agnostic, sort_cap, fast_cap;
-    int merge_ok;  // the dynamic shared memory includes the cluster merge's key lists (kGroups * max_det keys)
+    int all_general;  // nms_general_kernel: every image takes the general path (no class-split kernel ran)
+    int wait_tiles;   // nms_fast_kernel: spin on the image's scored-tile counter (the score kernel may still be running)
     float thr_f;
     double thr_d;
     CandWs ws;
@@ -832,420 +821,19 @@ __device__ __noinline__ void team_sort(unsigned long long *k, const int n, const
 
 constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a team of 8 warps
 
-// ---- one CTA per (image, class group) -------------------------------------------------------------
-// The score stage bucketed the image's candidates by class group (class & 3), recorded the max
-// coordinate and listed the cross boxes.  When the image qualifies for the fast path (class-aware,
-// not truncated by max_nms, every group <= fast_cap, offsets well separated, cross list complete)
-// the kGroups CTAs of the image sweep their classes independently:
-//   1. bucket -> class histogram -> counting scatter into class segments;
-//   2. sort every segment (large ones by teams of 8 warps, the rest one warp each), gather the boxes
-//      from L2 in sorted order, add the class offset, exact cross-class check against the cross list;
-//   3. greedy sweep, one work item per chunk of 32 boxes, items handed out in (class, chunk) order:
-//      a chunk tests its boxes against the keeps of every earlier chunk of its class as soon as that
-//      chunk is final (flag in shared memory), then settles its own 32 boxes and publishes its keeps —
-//      the chunks of a class pipeline across warps and only the settle step is serial;
-//   4. kept keys compacted (sorted and cut to max_det only when a group keeps more than that).
-// The kGroups CTAs of an image form one thread-block cluster: after a cluster barrier every CTA copies the other
-// groups' kept keys through distributed shared memory, ranks its own keys among all of them by counting
-// (rank = output row) and writes its rows.  Anything else — and any image where a cross-class pair suppresses — is
-// handled by one CTA with nms_image (exact general algorithm).
-__global__ void __cluster_dims__(kGroups, 1, 1) __launch_bounds__(kNmsThreads, 1) nms_group_kernel(const NmsParams p) {
+// ---- general path: one CTA per image that needs it ------------------------------------------------------
+// Launched after nms_fast_kernel (nms_fast.cuh).  An image is redone here, exactly, when the class-split kernel
+// raised its flag (max_nms truncation, a class group above its capacity, too many cross boxes, a cross-class pair
+// that suppresses, list overflows) or when the call as a whole cannot use the class split (`all_general`:
+// class-agnostic NMS, very large max_det, anchors beyond the fast key layout).
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_general_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
-    __shared__ int g_cnt[kMaxClasses], g_begin[kMaxClasses], g_cursor[kMaxClasses], g_order[kMaxClasses];
-    __shared__ int g_cum[kMaxClasses + 1];             // first sweep item of the oi-th largest class
-    __shared__ volatile int g_fin[kMaxClasses];        // chunks of the class that are final
-    __shared__ volatile int g_kcum[kFastCap / 32 + kMaxClasses];  // per sweep item: keeps of its class up to and including it
-    __shared__ int g_wbase[kFastCap / 32 + 1];
-    __shared__ int g_next, g_next2, g_fallback, g_nbig;
-    __shared__ unsigned x_minx[kMaxClasses], x_miny[kMaxClasses];  // per class: min x1 / y1 of its cross boxes (ordered uint)
-    __shared__ int c_kpub, c_fallback;               // read by the other CTAs of the cluster
-    __shared__ float4 x_box[kMaxCross];              // cross boxes, class offset applied
-    __shared__ unsigned long long x_key[kMaxCross];
-    const int g = blockIdx.x, b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NT = p.NT;
-    const size_t slot0 = (size_t)b * NT * kPpTile;
-    int *ctr = p.ws.ctr + b * kImgCtr;
-    long long *prof = p.prof ? p.prof + ((size_t)b * kGroups + g) * 16 : nullptr;
-#define GPROF(slot) do { if (prof && tid == 0) prof[slot] = clock64(); } while (0)
-    GPROF(0);
-
-    int total = 0, gmax = 0;
-#pragma unroll
-    for (int q = 0; q < kGroups; ++q) {
-        const int c = ctr[q];
-        total += c;
-        gmax = max(gmax, c);
-    }
-    const int xc = ctr[kGroups + 1];
-    const float span = ordered_float((unsigned)ctr[kGroups]) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
-    const bool per_class = !p.agnostic && 4 * (long long)total > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
-    const bool use_off = !p.agnostic && !per_class;
-    const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
-    const bool fast = !p.agnostic && total > 0 && total <= p.max_nms && gmax <= p.fast_cap && p.merge_ok &&
-                      (!use_off || (filter_ok && xc <= kMaxCross));
-    if (!fast) {
-        if (g == 0) {
-            NmsParams q = p;
-            q.prof = nullptr;
-            nms_image(q, b, nms_smem);
-            GPROF(7);
-        }
-        return;
-    }
-
-    // shared memory: keys[fast_cap] u64 | box_s[fast_cap] float4 | kept_s[fast_cap] float4 | keep_bits
-    // (kept_s first holds the staged bucket, later the compacted kept keys; the merge reuses everything)
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(nms_smem);
-    float4 *box_s = reinterpret_cast<float4 *>(nms_smem + (size_t)p.fast_cap * 8);
-    float4 *kept_s = reinterpret_cast<float4 *>(nms_smem + (size_t)p.fast_cap * 24);
-    unsigned long long *stage = reinterpret_cast<unsigned long long *>(kept_s);
-    unsigned *keep_bits = reinterpret_cast<unsigned *>(nms_smem + (size_t)p.fast_cap * 40);  // [fast_cap / 32 + 1]
-
-    const int n = ctr[g];
-    const unsigned long long *bucket = p.ws.gkey + ((size_t)b * kGroups + g) * ((size_t)NT * kPpTile);
-    if (tid < kMaxClasses) { g_cnt[tid] = 0; g_fin[tid] = 0; x_minx[tid] = 0xffffffffu; x_miny[tid] = 0xffffffffu; }
-    if (tid == 0) { g_next = 0; g_next2 = 0; g_fallback = 0; g_nbig = 0; }
-    for (int i = tid; i < (p.fast_cap >> 5) + 1; i += kNmsThreads) keep_bits[i] = 0u;
-    __syncthreads();
-    for (int i = tid; i < n; i += kNmsThreads) {
-        const unsigned long long key = bucket[i];
-        stage[i] = key;
-        atomicAdd(&g_cnt[key_class(key)], 1);
-    }
-    if (use_off && xc > 0 && tid < xc) {
-        float4 x = p.ws.xbox[(size_t)b * kMaxCross + tid];
-        const unsigned long long kx = p.ws.xkey[(size_t)b * kMaxCross + tid];
-        atomicMin(&x_minx[key_class(kx)], float_ordered(x.x));
-        atomicMin(&x_miny[key_class(kx)], float_ordered(x.y));
-        const float offx = (float)key_class(kx) * span;
-        x.x = x.x + offx; x.y = x.y + offx; x.z = x.z + offx; x.w = x.w + offx;
-        x_box[tid] = x;
-        x_key[tid] = kx;
-    }
-    __syncthreads();
-    GPROF(1);
-    // ---- class segments (exclusive prefix of the histogram) and the largest-first class order
-    if (warp == 0) {
-        int c4[4], sum = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { c4[u] = g_cnt[lane * 4 + u]; sum += c4[u]; }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        int run = inc - sum;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { g_begin[lane * 4 + u] = run; g_cursor[lane * 4 + u] = run; run += c4[u]; }
-    } else if (tid >= 32 && tid < 32 + kMaxClasses) {
-        const int c = tid - 32, nc = g_cnt[c];
-        int rank = 0;
-        for (int o = 0; o < kMaxClasses; ++o) {
-            const int m = g_cnt[o];
-            rank += (m > nc || (m == nc && o < c)) ? 1 : 0;
-        }
-        g_order[rank] = c;
-        if (nc > kTeamMin) atomicAdd(&g_nbig, 1);
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += kNmsThreads) {
-        const unsigned long long key = stage[i];
-        keys[atomicAdd(&g_cursor[key_class(key)], 1)] = key;
-    }
-    if (warp == 1) {  // sweep items: exclusive prefix of the chunk counts in class order
-        int c4[4], sum = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { c4[u] = (g_cnt[g_order[lane * 4 + u]] + 31) >> 5; sum += c4[u]; }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        int run = inc - sum;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { g_cum[lane * 4 + u] = run; run += c4[u]; }
-        if (lane == 31) g_cum[kMaxClasses] = inc;
-    }
-    __syncthreads();
-    GPROF(2);
-    const bool xcheck = use_off && xc > 0;
-    const int nbig = g_nbig;
-
-    // ---- sort + gather: class `oi` of the size order.  After the sort the boxes are fetched from L2 in
-    // sorted order, the exact cross-class check runs on the few boxes near the far corner, and the class
-    // offset is added (tv:ops/boxes.py:100-101, separate roundings).
-    auto gather_class = [&](const int c, const int s, const int nc, const int t0, const int tstride) {
-        const float off = use_off ? (float)c * span : 0.f;
-        // A box of class c meets a cross box of a class k > c only if its x2 / y2 exceed
-        // (min x1 / y1 of that class's cross boxes) + (k - c) * span (rounding: < 1): per-class limits.
-        float lim_x = 3.0e38f, lim_y = 3.0e38f;
-        if (xcheck) {
-#pragma unroll
-            for (int u = 0; u < kMaxClasses / 32; ++u) {
-                const int k = lane + 32 * u;
-                const unsigned ox = x_minx[k];
-                if (k > c && ox != 0xffffffffu) {
-                    const float d = (float)(k - c) * span - 1.0f;
-                    lim_x = fminf(lim_x, ordered_float(ox) + d);
-                    lim_y = fminf(lim_y, ordered_float(x_miny[k]) + d);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lim_x = fminf(lim_x, __shfl_xor_sync(0xffffffffu, lim_x, o));
-                lim_y = fminf(lim_y, __shfl_xor_sync(0xffffffffu, lim_y, o));
-            }
-        }
-        for (int i0 = t0; i0 < nc; i0 += 4 * tstride) {  // 4 independent gathers in flight per thread
-            float4 bx[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * tstride;
-                if (i < nc) bx[u] = p.ws.box[slot0 + key_slot(keys[s + i])];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * tstride;
-                if (i < nc) {
-                    float4 y = bx[u];
-                    const bool near_corner = xcheck && y.z > lim_x && y.w > lim_y;
-                    y.x = y.x + off; y.y = y.y + off; y.z = y.z + off; y.w = y.w + off;
-                    box_s[s + i] = y;
-                    if (near_corner) {
-                        const unsigned long long ky = keys[s + i];
-                        for (int q = 0; q < xc; ++q) {
-                            const unsigned long long kx = x_key[q];
-                            if (key_class(kx) <= c) continue;  // the pair is found from the lower class's side
-                            const float4 x = x_box[q];
-                            if (!(x.x < y.z && x.y < y.w && y.x < x.z && y.y < x.w)) continue;  // no overlap: quotient 0
-                            const bool x_first = (kx & kOrderMask) < (ky & kOrderMask);
-                            if (x_first ? suppresses(x, y, p.flavor, p.thr_f, p.thr_d) : suppresses(y, x, p.flavor, p.thr_f, p.thr_d))
-                                g_fallback = 1;
-                        }
-                    }
-                }
-            }
-        }
-    };
-    {
-        const int team = warp >> 3, tw = warp & 7;
-        for (int oi = team; oi < nbig; oi += 4) {  // large classes: one team of 8 warps each
-            const int c = g_order[oi], nc = g_cnt[c], s = g_begin[c];
-            team_sort(keys + s, nc, tw, 1 + team);
-            gather_class(c, s, nc, tw * 32 + lane, 256);
-        }
-        for (;;) {  // the rest: one warp each, largest first
-            int oi = 0;
-            if (lane == 0) oi = nbig + atomicAdd(&g_next, 1);
-            oi = __shfl_sync(0xffffffffu, oi, 0);
-            if (oi >= kMaxClasses) break;
-            const int c = g_order[oi], nc = g_cnt[c];
-            if (nc == 0) break;
-            const int s = g_begin[c];
-            warp_sort(keys + s, nc);
-            gather_class(c, s, nc, lane, 32);
-        }
-    }
-    if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 8), (unsigned long long)clock64());
-    __syncthreads();
-
-    // ---- sweep: one item per chunk of 32 boxes, handed out in (class, chunk) order
-    const int n_items = g_cum[kMaxClasses];
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(&g_next2, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
-        int lo = 0, hi = kMaxClasses;  // g_cum[lo] <= item < g_cum[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (g_cum[mid] <= item) lo = mid; else hi = mid;
-        }
-        const int c = g_order[lo], s = g_begin[c], nc = g_cnt[c];
-        const int j = item - g_cum[lo], item0 = g_cum[lo];
-        const int i = s + 32 * j + lane;
-        const bool valid = 32 * j + lane < nc;
-        const float4 bx = valid ? box_s[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        bool dead = !valid;
-        int K = 0;
-        for (int jj = 0; jj < j; ++jj) {
-            while (g_fin[c] <= jj) __nanosleep(20);
-            __threadfence_block();  // the chunk's keeps (kept_s, g_kcum) were written before its flag
-            const int Knew = g_kcum[item0 + jj];
-            for (int k = K; k < Knew; k += 4) {
-                if (__all_sync(0xffffffffu, dead)) break;  // dense clusters die against the first keeps
-                // 4 independent tests per trip (entries past Knew: masked)
-                const float4 k0 = kept_s[s + k], k1 = kept_s[s + k + 1], k2 = kept_s[s + k + 2], k3 = kept_s[s + k + 3];
-                const bool s0 = suppresses(k0, bx, p.flavor, p.thr_f, p.thr_d);
-                const bool s1 = k + 1 < Knew && suppresses(k1, bx, p.flavor, p.thr_f, p.thr_d);
-                const bool s2 = k + 2 < Knew && suppresses(k2, bx, p.flavor, p.thr_f, p.thr_d);
-                const bool s3 = k + 3 < Knew && suppresses(k3, bx, p.flavor, p.thr_f, p.thr_d);
-                dead = dead || s0 || s1 || s2 || s3;
-            }
-            K = Knew;
-        }
-        // settle the chunk: lowest surviving lane == best remaining score: kept (stops at max_det keeps:
-        // later boxes of the class cannot reach the output)
-        unsigned alive = __ballot_sync(0xffffffffu, !dead);
-        unsigned keepm = 0u;
-        int room = p.max_det - K;
-        while (alive && room > 0) {
-            const int jl = __ffs(alive) - 1;
-            keepm |= 1u << jl;
-            alive &= ~(1u << jl);
-            --room;
-            if (!alive) break;
-            const float4 jb = make_float4(__shfl_sync(0xffffffffu, bx.x, jl), __shfl_sync(0xffffffffu, bx.y, jl),
-                                          __shfl_sync(0xffffffffu, bx.z, jl), __shfl_sync(0xffffffffu, bx.w, jl));
-            const bool sup = ((alive >> lane) & 1u) && suppresses(jb, bx, p.flavor, p.thr_f, p.thr_d);
-            alive &= ~__ballot_sync(0xffffffffu, sup);
-        }
-        if ((keepm >> lane) & 1u) kept_s[s + K + __popc(keepm & ((1u << lane) - 1u))] = bx;
-        if (lane == 0) {
-            if (keepm) {
-                const int c0 = s + 32 * j, w = c0 >> 5, sh = c0 & 31;
-                atomicOr(&keep_bits[w], keepm << sh);
-                if (sh && (keepm >> (32 - sh))) atomicOr(&keep_bits[w + 1], keepm >> (32 - sh));
-            }
-            g_kcum[item] = K + __popc(keepm);
-        }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) g_fin[c] = j + 1;
-    }
-    if (prof && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(prof + 3), (unsigned long long)clock64());
-    __syncthreads();
-
-    // ---- kept keys of the group: class stripped, compacted (sorted and cut to max_det only if there are more)
-    unsigned long long *keys2 = reinterpret_cast<unsigned long long *>(box_s);
-    const int nwords = (n + 31) >> 5;
-    if (warp == 0) {
-        int c4[4], sum = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int w = lane * 4 + u;
-            c4[u] = w < nwords ? __popc(keep_bits[w]) : 0;
-            sum += c4[u];
-        }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        int run = inc - sum;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { g_wbase[lane * 4 + u] = run; run += c4[u]; }
-        if (lane == 31) g_wbase[kFastCap / 32] = inc;
-    }
-    __syncthreads();
-    const int Kg = g_wbase[kFastCap / 32];
-    for (int i = tid; i < n; i += kNmsThreads) {
-        const unsigned wbits = keep_bits[i >> 5];
-        if ((wbits >> (i & 31)) & 1u)
-            keys2[g_wbase[i >> 5] + __popc(wbits & ((1u << (i & 31)) - 1u))] = keys[i] & kOrderMask;
-    }
-    if (Kg > p.max_det) {  // rare: only the group's first max_det keeps in global order can reach the output
-        int n2 = 64;
-        while (n2 < Kg) n2 <<= 1;
-        for (int i = Kg + tid; i < n2; i += kNmsThreads) keys2[i] = ~0ull;
-        __syncthreads();
-        block_sort(keys2, n2);
-    }
-    const int Kpub = min(Kg, p.max_det);
-    if (tid == 0) { c_kpub = Kpub; c_fallback = g_fallback; }
-    GPROF(4);
-    // ---- merge across the image's kGroups CTAs (one thread-block cluster) through distributed shared memory:
-    // every CTA copies the other groups' kept keys, ranks its own keys among all of them by counting (keys
-    // are distinct: rank = number of smaller keys = row of the output) and writes its own rows.
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    GPROF(5);
-    unsigned long long *allk = reinterpret_cast<unsigned long long *>(nms_smem + nms_group_merge_offset(p.fast_cap));
-    int kq[kGroups], total_k = 0, fb = 0;
-#pragma unroll
-    for (int q = 0; q < kGroups; ++q) {
-        kq[q] = *cluster.map_shared_rank(&c_kpub, q);
-        fb |= *cluster.map_shared_rank(&c_fallback, q);
-        total_k += kq[q];
-    }
-    {
-        int base = 0;
-#pragma unroll
-        for (int q = 0; q < kGroups; ++q) {
-            const unsigned long long *src = cluster.map_shared_rank(keys2, q);
-            for (int i = tid; i < kq[q]; i += kNmsThreads) allk[base + i] = src[i];
-            base += kq[q];
-        }
-        for (int i = total_k + tid; i < ((total_k + 63) & ~63); i += kNmsThreads) allk[i] = ~0ull;
-    }
-    cluster.sync();  // nobody reads another CTA's shared memory past this point (also a CTA barrier)
-    GPROF(6);
-    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = xc; prof[13] = 1; }
-    if (fb) {
-        // a pair of different classes suppresses: the exact global sweep redoes the image
-        if (g == 0) {
-            NmsParams q = p;
-            q.prof = nullptr;
-            nms_image(q, b, nms_smem);
-            if (prof && tid == 0) prof[14] = 1;
-        }
-        GPROF(7);
-        return;
-    }
-    const int nkept = min(total_k, p.max_det);
-    // rank of every own key = number of smaller keys in all lists (padded with +inf to a multiple of 64):
-    // 8 threads per key, 8 independent compares per trip; the key's record is fetched while the count runs
-    constexpr int kSubT = 8;
-    const int total_pad = (total_k + 63) & ~63;
-    for (int i0 = 0; i0 < Kpub; i0 += kNmsThreads / kSubT) {
-        const int i = i0 + tid / kSubT, sub = tid % kSubT;
-        const bool owner = i < Kpub && sub == 0;
-        const unsigned long long key = i < Kpub ? keys2[i] : 0ull;
-        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-        int meta = 0;
-        float sc = 0.f;
-        if (owner) {
-            const int slot = key_slot(key);
-            bx = p.ws.box[slot0 + slot];
-            meta = p.ws.meta[slot0 + slot];
-            sc = p.ws.score[slot0 + slot];
-        }
-        int rank = 0;
-        if (i < Kpub) {
-            for (int j = sub; j < total_pad; j += 8 * kSubT) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) rank += allk[j + u * kSubT] < key ? 1 : 0;
-            }
-        }
-#pragma unroll
-        for (int o = 1; o < kSubT; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
-        if (owner && rank < nkept) {
-            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + rank) * 6);
-            d[0] = make_float2(bx.x, bx.y);
-            d[1] = make_float2(bx.z, bx.w);
-            d[2] = make_float2(sc, (float)(meta >> 24));
-            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = meta & 0xffffff;
-        }
-    }
-    if (g == 0) {
-        for (int i = nkept + tid; i < p.max_det; i += kNmsThreads) {
-            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
-            d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
-            if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
-        }
-        if (tid == 0) p.counts[b] = nkept;
-    }
-    GPROF(7);
-#undef GPROF
-}
-
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    nms_image(p, blockIdx.x, nms_smem);
+    // programmatic dependent launch: the CTAs may be scheduled while the previous kernel drains; everything below
+    // needs its results
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int b = blockIdx.x;
+    if (!p.all_general && __ldcg(&p.ws.ctr[b * kImgCtr + kCtrGeneral]) == 0) return;
+    nms_image(p, b, nms_smem);
 }
 
 }  // namespace plyolo

@@ -10,11 +10,16 @@
 //   first argmax over the sigmoid VALUES (T1) inside the rounding window of the fp32 sigmoid;
 //   conf = sigmoid(obj) * class_conf, conf >= thr in fp32.  The survivors are compacted IN ANCHOR ORDER (warp
 //   ballot + prefix) into the tile's slot range of the candidate arrays and bucketed by class group.
-// Stage 2  nms_group_kernel      one 4-CTA cluster per image (nms.cuh), latency-bound: per-class sorts and greedy
-//   sweeps with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division; see
-//   `suppresses`), kept lists merged by rank through distributed shared memory; nms_image (one CTA, global sort +
-//   bit-matrix rounds) for everything the class split cannot handle exactly.
+// Stage 2  nms_fast_kernel       one 4-CTA cluster per image (nms_fast.cuh), launched with programmatic dependent
+//   launch so that it runs UNDER stage 1: small CTAs (512 threads, 52 KB) co-resident with the score CTAs, every
+//   cluster starts when its image's scored-tile counter is complete.  Per-class pre-kill, sorts and greedy sweeps
+//   with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division; see `suppresses`),
+//   kept lists merged by rank through distributed shared memory.
+// Stage 3  nms_general_kernel    one CTA per image (nms.cuh: global sort + bit-matrix rounds), only for the images
+//   the class split cannot handle exactly (flag per image; exits at once otherwise).
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
@@ -26,7 +31,12 @@ constexpr int kPpTile = 128;
 constexpr int kGroups = 4;      // class groups per image (class & 3): one NMS CTA each
 constexpr int kMaxCross = 512;  // boxes that may reach into another class's offset range (x1, y1 < -0.5)
 constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
-constexpr int kImgCtr = 8;      // ints per image in the counter block (zeroed before every call)
+constexpr int kImgCtr = 16;     // ints per image in the counter block (zeroed before every call)
+constexpr int kCtrGeneral = 6;  // counter block: the image must be redone by the general path
+constexpr int kCtrDone = 7;     // counter block: tiles of the image that have been scored (released by the score kernel)
+constexpr int kCtrMaxX2 = 8;    // counter block: largest x2 / y2 of the image's candidates (ordered uint): bounds which
+constexpr int kCtrMaxY2 = 9;    //   cross boxes can reach another class's offset range at all
+constexpr int kBucketCap = 1536;  // bucket entries kept per (image, class group) == kFastCapG of nms_fast.cuh
 
 constexpr size_t kNmsSmemLimit = 190 * 1024;  // dynamic shared memory of the NMS kernels (33 KB are static)
 struct CandWs {
@@ -35,8 +45,9 @@ struct CandWs {
     float *score;       // [B, NT*128]
     int *meta;          // [B, NT*128]  anchor | class << 24
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
-    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | (unused)
-    unsigned long long *gkey;     // [B, kGroups, NT*128]  class << 57 | ~ordered(score) << 25 | slot
+    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | general | tiles done | max x2 | max y2
+    unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | slot
+    float4 *gbox;                 // [B, kGroups, kBucketCap]  the same candidates' corners
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
 };
@@ -56,7 +67,7 @@ struct TileShared {
     int warp_cnt[kPpTile / 32];
     int g_wcnt[kPpTile / 32][kGroups];
     int g_base[kGroups];
-    float w_max[kPpTile / 32];
+    float w_max[kPpTile / 32], w_maxz[kPpTile / 32], w_maxw[kPpTile / 32];
 };
 
 struct TileCoord {
@@ -239,9 +250,14 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         if (grp == g) gm = mg;
     }
     float cm = pass ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -3.0e38f;
+    float cz = pass ? box.z : -3.0e38f, cw = pass ? box.w : -3.0e38f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
-    if (lane == 0) sh.w_max[warp] = cm;
+    for (int o = 16; o > 0; o >>= 1) {
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        cz = fmaxf(cz, __shfl_xor_sync(0xffffffffu, cz, o));
+        cw = fmaxf(cw, __shfl_xor_sync(0xffffffffu, cw, o));
+    }
+    if (lane == 0) { sh.w_max[warp] = cm; sh.w_maxz[warp] = cz; sh.w_maxw[warp] = cw; }
     group_barrier(bar_id);
     TPROF(4);
     int base = 0, total = 0;
@@ -268,11 +284,12 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
 #pragma unroll
         for (int w = 0; w < kPpTile / 32; ++w) n += sh.g_wcnt[w][tid];
         sh.g_base[tid] = n ? atomicAdd(&ctr[tid], n) : 0;
-    } else if (tid == 32) {
-        float mx = sh.w_max[0];
+    } else if (tid >= 32 && tid < 35) {
+        const float *wm = tid == 32 ? sh.w_max : (tid == 33 ? sh.w_maxz : sh.w_maxw);
+        float mx = wm[0];
 #pragma unroll
-        for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, sh.w_max[w]);
-        atomicMax(reinterpret_cast<unsigned *>(&ctr[kGroups]), float_ordered(mx));
+        for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, wm[w]);
+        atomicMax(reinterpret_cast<unsigned *>(&ctr[tid == 32 ? kGroups : (tid == 33 ? kCtrMaxX2 : kCtrMaxY2)]), float_ordered(mx));
     }
     group_barrier(bar_id);
     TPROF(5);
@@ -281,7 +298,10 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         for (int w = 0; w < warp; ++w) pos += sh.g_wcnt[w][grp];
         const unsigned long long key = ((unsigned long long)cls << 57) |
                                        ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)islot;
-        p.ws.gkey[((size_t)b * kGroups + grp) * ((size_t)p.NT * kPpTile) + pos] = key;
+        if (pos < kBucketCap) {  // a fuller group is redone by the general path from the slot arrays
+            p.ws.gkey[((size_t)b * kGroups + grp) * kBucketCap + pos] = key;
+            p.ws.gbox[((size_t)b * kGroups + grp) * kBucketCap + pos] = box;
+        }
         if (box.x < -0.5f && box.y < -0.5f) {
             const int xi = atomicAdd(&ctr[kGroups + 1], 1);
             if (xi < kMaxCross) {
@@ -358,10 +378,24 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *m
         : "memory");
 }
 
+// the scored-tile counter of an image: release at GPU scope (the tile's candidate records were written by the whole
+// group before the group barrier that precedes this call); nms_fast_kernel acquires it
+__device__ __forceinline__ void publish_tile(int *ctr) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ctr + kCtrDone) : "memory");
+}
+
+// kScoreRegs registers per thread leave room on the SM for the co-resident NMS CTA (budget: see nms_fast.cuh)
+#ifndef PLYOLO_SCORE_REGS
+#define PLYOLO_SCORE_REGS 64
+#endif
+constexpr int kScoreRegs = PLYOLO_SCORE_REGS;
+
 template <bool FUSED>
-__global__ void __launch_bounds__(kScoreThreads, 1)
+__global__ void __maxnreg__(kScoreRegs)
 score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const int use_tmap) {
     extern __shared__ __align__(128) float stages[];  // [kStages][ch * 128]
+    // programmatic dependent launch: the NMS grid may be scheduled from now on (its clusters wait for their image)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
     __shared__ TileShared sh[kConsumers];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -437,18 +471,21 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
                 group_barrier(1 + grp);
                 if (gtid == 0) mbar_arrive(&empty_bar[s]);
             }, acc, tw1);
+            group_barrier(1 + grp);  // every record of the tile has been issued
+            if (gtid == 0) publish_tile(p.ws.ctr + tc.b * kImgCtr);
         }
     }
 }
 
 }  // namespace plyolo
 
-#include "nms.cuh"
+#include "nms_fast.cuh"
 
 namespace plyolo {
 
 static thread_local long long *g_nms_prof = nullptr;
 static thread_local long long *g_score_prof = nullptr;
+static thread_local bool g_skip_nms = false;
 
 static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t off = 0;
@@ -459,7 +496,8 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t o_box = take(slots * sizeof(float4));
     size_t o_sc = take(slots * sizeof(float));
     size_t o_meta = take(slots * sizeof(int));
-    size_t o_gkey = take(slots * kGroups * sizeof(unsigned long long));
+    size_t o_gkey = take((size_t)B * kGroups * kBucketCap * sizeof(unsigned long long));
+    size_t o_gbox = take((size_t)B * kGroups * kBucketCap * sizeof(float4));
     size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
     size_t o_xbox = take((size_t)B * kMaxCross * sizeof(float4));
     if (ws) {
@@ -469,6 +507,7 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
         ws->score = reinterpret_cast<float *>(base + o_sc);
         ws->meta = reinterpret_cast<int *>(base + o_meta);
         ws->gkey = reinterpret_cast<unsigned long long *>(base + o_gkey);
+        ws->gbox = reinterpret_cast<float4 *>(base + o_gbox);
         ws->xkey = reinterpret_cast<unsigned long long *>(base + o_xkey);
         ws->xbox = reinterpret_cast<float4 *>(base + o_xbox);
     }
@@ -477,34 +516,6 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
 
 // worst-case tile count for A anchors split into at most PLYOLO_MAX_LEVELS levels
 static int max_tiles(int A) { return (A + kPpTile - 1) / kPpTile + PLYOLO_MAX_LEVELS; }
-
-static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
-                   const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, cudaStream_t stream) {
-    NmsParams np;
-    np.B = B; np.NT = NT; np.max_nms = max_nms; np.max_det = max_det; np.flavor = flavor;
-    np.agnostic = class_agnostic ? 1 : 0;
-    np.thr_f = (float)nms_thre; np.thr_d = nms_thre;
-    int cap = 64;
-    const int need = max_nms < A ? max_nms : A;
-    while (cap < need) cap <<= 1;
-    np.sort_cap = cap;
-    np.fast_cap = cap < kFastCap ? cap : kFastCap;
-    np.ws = ws; np.dets = dets; np.counts = counts; np.keep_idx = keep_idx;
-    np.prof = g_nms_prof;
-    size_t smem = nms_group_smem_bytes(cap, np.fast_cap, max_det, NT);
-    np.merge_ok = 1;
-    if (smem > kNmsSmemLimit) {  // very large max_det: no room for the merge lists, the images take the single-CTA path
-        smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
-        np.merge_ok = 0;
-    }
-    PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
-    cudaFuncSetAttribute(nms_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    record_stage_event(1, stream);
-    nms_group_kernel<<<dim3(kGroups, B), kNmsThreads, smem, stream>>>(np);
-    PLYOLO_CHECK_LAUNCH("nms_group_kernel");
-    record_stage_event(2, stream);
-    return PLYOLO_OK;
-}
 
 static int sm_count() {
     static thread_local int n = 0;
@@ -516,18 +527,128 @@ static int sm_count() {
     return n;
 }
 
-// zeroes the per-image counters, then scores every tile (persistent TMA pipeline; plain-load kernel if unaligned)
+// Per-device, once: the kernels' shared-memory limits (fixed maxima, so that no launch ever lowers another thread's
+// limit) and the maximal shared-memory carveout — the score CTA (171.5 KB) and the NMS CTA (53.5 KB) only fit on
+// one SM together when the SM is configured for 228 KB of shared memory.
+constexpr size_t kScoreSmemLimit = (size_t)kStages * kPpTile * (5 + PLYOLO_MAX_CLASSES) * sizeof(float);  // 192 KB
+static int ensure_kernel_attributes() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return PLYOLO_OK;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void *fn, size_t smem) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    };
+    set((const void *)score_kernel<true>, kScoreSmemLimit);
+    set((const void *)score_kernel<false>, kScoreSmemLimit);
+    set((const void *)score_kernel_simple<true>, kScoreSmemLimit / kStages);
+    set((const void *)score_kernel_simple<false>, kScoreSmemLimit / kStages);
+    set((const void *)nms_fast_kernel, kFastSmemBytes);
+    set((const void *)nms_general_kernel, kNmsSmemLimit);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PLYOLO_ERR_CUDA;
+    }
+    done[dev] = true;
+    return PLYOLO_OK;
+}
+
+// PLYOLO_NO_PDL=1 launches the NMS kernels as plain stream-ordered kernels (A/B measurements, debugging)
+static bool pdl_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("PLYOLO_NO_PDL");
+        return !(v && v[0] == '1');
+    }();
+    return on;
+}
+
+template <typename... Args>
+static cudaError_t launch_ex(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                             Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// `overlap`: the score stage was the persistent kernel (it triggers its dependents at once and publishes the
+// per-image scored-tile counters), so the class-split NMS may start under it.
+static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
+                   const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream) {
+    NmsParams np;
+    np.B = B; np.NT = NT; np.max_nms = max_nms; np.max_det = max_det; np.flavor = flavor;
+    np.agnostic = class_agnostic ? 1 : 0;
+    np.thr_f = (float)nms_thre; np.thr_d = nms_thre;
+    int cap = 64;
+    const int need = max_nms < A ? max_nms : A;
+    while (cap < need) cap <<= 1;
+    np.sort_cap = cap;
+    np.fast_cap = cap < kFastCap ? cap : kFastCap;
+    np.ws = ws; np.dets = dets; np.counts = counts; np.keep_idx = keep_idx;
+    np.prof = g_nms_prof;
+    const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
+    PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
+    // the class-split kernel: class-aware NMS, max_det within its kept-key lists, slots within its key layout
+    const bool split = !class_agnostic && max_det <= kFastMaxDet && (long long)NT * kPpTile <= (1ll << kFastSlotBits) &&
+                       !g_skip_nms;
+    const bool pdl = pdl_enabled();
+    record_stage_event(1, stream);
+    if (g_skip_nms) return PLYOLO_OK;  // debug: time the score stage alone
+    if (split) {
+        np.wait_tiles = overlap ? 1 : 0;
+        np.all_general = 0;
+        const cudaError_t e = launch_ex(nms_fast_kernel, dim3(kGroups, B), dim3(kFastThreads), kFastSmemBytes, stream,
+                                        pdl && overlap, np);
+        if (e != cudaSuccess) {
+            set_error("nms_fast_kernel: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+            return PLYOLO_ERR_CUDA;
+        }
+        count_launch();
+    }
+    static const bool no_general = [] { const char *v = getenv("PLYOLO_DEBUG_NO_GENERAL"); return v && v[0] == '1'; }();
+    if (split && no_general) return PLYOLO_OK;  // debug: measures what the (normally idle) general kernel costs
+    np.wait_tiles = 0;
+    np.all_general = split ? 0 : 1;
+    np.prof = nullptr;
+    const cudaError_t e = launch_ex(nms_general_kernel, dim3(B), dim3(kNmsThreads), smem, stream, pdl && split, np);
+    if (e != cudaSuccess) {
+        set_error("nms_general_kernel: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PLYOLO_ERR_CUDA;
+    }
+    count_launch();
+    record_stage_event(2, stream);
+    return PLYOLO_OK;
+}
+
+// zeroes the per-image counters, then scores every tile (persistent TMA pipeline; plain-load kernel if unaligned).
+// *overlap = the persistent kernel ran (dependent launch trigger + scored-tile counters).
 template <bool FUSED>
-static int launch_score(const ScoreParams &sp, cudaStream_t stream) {
+static int launch_score(const ScoreParams &sp, cudaStream_t stream, bool *overlap) {
+    int rc = ensure_kernel_attributes();
+    if (rc != PLYOLO_OK) return rc;
     if (cudaMemsetAsync(sp.ws.ctr, 0, (size_t)sp.B * kImgCtr * sizeof(int), stream) != cudaSuccess) {
         set_error("cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
         return PLYOLO_ERR_CUDA;
     }
     const size_t tile_b = (size_t)kPpTile * sp.ch * sizeof(float);
     record_stage_event(0, stream);
+    *overlap = sp.bulk_ok != 0;
     if (sp.bulk_ok) {
         const size_t smem = tile_b * kStages;
-        cudaFuncSetAttribute(score_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int total = sp.NT * sp.B, sms = sm_count();
         TmapPack pack;
         memset(&pack, 0, sizeof(pack));
@@ -564,7 +685,6 @@ static int launch_score(const ScoreParams &sp, cudaStream_t stream) {
         score_kernel<FUSED><<<(total + 1) / 2 < sms ? (total + 1) / 2 : sms, kScoreThreads, smem, stream>>>(sp, pack, use_tmap);
         PLYOLO_CHECK_LAUNCH("score_kernel");
     } else {
-        if (tile_b > 48 * 1024) cudaFuncSetAttribute(score_kernel_simple<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_b);
         score_kernel_simple<FUSED><<<dim3(sp.NT, sp.B), kPpTile, tile_b, stream>>>(sp);
         PLYOLO_CHECK_LAUNCH("score_kernel_simple");
     }
@@ -595,6 +715,8 @@ static int check_post_args(int B, int A, int C, int max_nms, int max_det, int fl
 // timestamps for the calling thread's next launches; null switches it off
 extern "C" void plyolo_debug_score_profile(void *device_buf) { plyolo::g_score_prof = static_cast<long long *>(device_buf); }
 extern "C" void plyolo_debug_nms_profile(void *device_buf) { plyolo::g_nms_prof = static_cast<long long *>(device_buf); }
+// debug hook: the calling thread's next postprocess calls stop after the score stage (bench.py times it alone)
+extern "C" void plyolo_debug_skip_nms(int on) { plyolo::g_skip_nms = on != 0; }
 
 extern "C" size_t plyolo_postprocess_workspace_bytes(int B, int A) {
     if (B < 1 || A < 1) return 0;
@@ -619,10 +741,11 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.prof = nullptr;
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
-    rc = launch_score<false>(sp, (cudaStream_t)stream);
+    bool overlap = false;
+    rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   (cudaStream_t)stream);
+                   overlap, (cudaStream_t)stream);
 }
 
 extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
@@ -647,8 +770,9 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     sp.bulk_ok = bulk ? 1 : 0;
     sp.prof = g_score_prof;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
-    rc = launch_score<true>(sp, (cudaStream_t)stream);
+    bool overlap = false;
+    rc = launch_score<true>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   (cudaStream_t)stream);
+                   overlap, (cudaStream_t)stream);
 }

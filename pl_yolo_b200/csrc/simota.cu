@@ -44,6 +44,7 @@ constexpr int kPrefetchRows = 2;  // L2 prefetch of the in-both anchors' predict
 constexpr bool kTightAll = true;  // tight lower bounds for every pair up front (else: only for pairs the cheap bound cannot prune)
 constexpr int kExtraEval = 1;    // exact costs evaluated beyond k in the first round (tightens the pruning bound)
 constexpr int kMaxConf = 128;     // conflicts one CTA can create (<= 11 per GT)
+constexpr int kTinyWindow = 2048; // candidates per pass of the tiny-GT search
 
 struct SimParams {
     const float *preds;
@@ -771,6 +772,12 @@ struct MatchShared {
     unsigned short clist[kGtPerCta * kMaxBoth];    // pairs whose cheap lower bound does not exceed U
     unsigned short elist[kGtPerCta * kMaxBoth];    // (GT, anchor slot) pairs whose exact cost is wanted
     unsigned char state[kGtPerCta][kMaxBoth];      // 0 = lower bound only, 1 = queued, 2 = exact cost known
+    // tiny GTs (fewer in-both anchors than k): CTA-wide search over the candidates whose cost carries +1e5
+    int tiny[kGtPerCta], ntiny, tn;
+    unsigned long long wmin[kMatchWarps];
+    unsigned long long tpick[16];                  // the `need` smallest lower-bound keys, then their exact cost keys
+    unsigned short tlist[kTinyWindow];             // candidates of the window whose lower bound does not exceed U
+    unsigned long long tkey[kTinyWindow];          // their exact (cost, anchor) keys
 };
 
 __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimParams p) {
@@ -791,7 +798,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     const int *ca = p.cand_anchor + (size_t)b * p.A;
     // ATen picks a 64-wide block for sum(-1) when the [G,Nc] output has fewer than 16 elements (and C >= 64)
     const bool wide = (long long)G * Nc < 16 && p.C >= 64;
-    if (tid == 0) sh.nconf = 0;
+    if (tid == 0) { sh.nconf = 0; sh.ntiny = 0; }
     long long *prof = p.prof ? p.prof + ((size_t)b * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define SPROF(slot) do { if (prof) { __syncthreads(); if (tid == 0) prof[slot] = clock64(); } } while (0)
     SPROF(0);
@@ -1086,31 +1093,111 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
                 }
                 __syncwarp();
             }
-            if (k > nb) {
-                // ---- tiny GT: fewer in-both anchors than k.  The remaining picks come from the candidates
-                // whose cost carries +1e5 (quantised to 1/128, T8): smallest (cost, anchor) over all others.
-                const short *rect = p.rect + ((size_t)b * p.Lmax + g) * p.n_levels * 8;
-                const int need = k - nb;  // <= 10
-                unsigned long long mine = ~0ull;  // lanes 0..need-1 hold the `need` smallest keys, ascending
-                for (int n = 0; n < Nc; ++n) {
-                    const int a = ca[n];
-                    int l, x, y;
-                    anchor_cell(p, a, l, x, y);
-                    if (in_both(rect + l * 8, x, y)) continue;
-                    float iou;
-                    float c = pair_cost(p, b, a, gx, gy, gw, gh, gc, false, wide, lane, sh.terms[warp], &iou);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    const unsigned long long key = ((unsigned long long)float_ordered(c) << 32) | (unsigned)a;
+            // tiny GT: fewer in-both anchors than k — the remaining picks are searched by the whole CTA below
+            if (k > nb && lane == 0) sh.tiny[atomicAdd(&sh.ntiny, 1)] = gi;
+        }
+    }
+
+    // ---- 3b. tiny GTs: the remaining k - nb picks come from the candidates whose cost carries +1e5 (quantised to
+    // 1/128, T8): the smallest (cost, anchor) over all candidates that are not in-both.  Whole CTA per GT:
+    //   lb(n) = fl(3 L_iou + 1e5) <= cost(n) (the class cost is >= 0, fp32 addition is monotone) from the candidate's
+    //   corner box alone;  the `need` smallest lb -> their exact costs -> U = the largest of them, an upper bound of
+    //   the need-th smallest cost;  every candidate with lb <= U gets its exact 80-class cost (one warp each), the
+    //   need smallest exact keys win.  Exact for any input; cheap because only boxes that overlap the GT about as
+    //   well as the best ones can have lb <= U.
+    __syncthreads();
+    for (int job = 0; job < sh.ntiny; ++job) {
+        const int q = sh.tiny[job], nbq = sh.nb[q], need = sh.k[q] - nbq, gq = sh.gidx[q];  // need <= 10
+        const float *Lq = p.labels + ((size_t)b * p.Lmax + gq) * 5;
+        const int qc = (int)Lq[0];
+        const float qx = Lq[1], qy = Lq[2], qw = Lq[3], qh = Lq[4];
+        const float q_x1 = qx - qw / 2, q_y1 = qy - qh / 2, q_x2 = qx + qw / 2, q_y2 = qy + qh / 2, q_area = qw * qh;
+        const float4 *cb = p.cand_box + (size_t)b * p.A;
+        const float *car = p.cand_area + (size_t)b * p.A;
+        // lower-bound key of candidate n; false: the candidate is in-both (its cost was handled above)
+        auto lb_key = [&](const int n, unsigned long long &key) -> bool {
+            const int a = __ldg(ca + n);
+            for (int i = 0; i < nbq; ++i)
+                if (sh.anchor[q][i] == a) return false;
+            const float4 c = __ldg(cb + n);  // the candidate-side operands of bboxes_iou, as the prep kernel formed them
+            const float tlx = fmaxf(q_x1, c.x), tly = fmaxf(q_y1, c.y), brx = fminf(q_x2, c.z), bry = fminf(q_y2, c.w);
+            const float en = (tlx < brx ? 1.f : 0.f) * (tly < bry ? 1.f : 0.f);
+            const float area_i = ((brx - tlx) * (bry - tly)) * en;
+            const float iou = area_i / ((q_area + __ldg(car + n)) - area_i);
+            const float liou = -logf(iou + 1e-8f);
+            const float lb = (0.0f + 3.0f * liou) + 100000.0f;
+            key = ((unsigned long long)float_ordered(lb) << 32) | (unsigned)a;
+            return true;
+        };
+        auto block_min = [&](unsigned long long v) -> unsigned long long {  // every thread gets the CTA-wide minimum
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+                v = other < v ? other : v;
+            }
+            if (lane == 0) sh.wmin[warp] = v;
+            __syncthreads();
+            v = sh.wmin[0];
+#pragma unroll
+            for (int w = 1; w < kMatchWarps; ++w) v = sh.wmin[w] < v ? sh.wmin[w] : v;
+            __syncthreads();
+            return v;
+        };
+        // (a) the `need` smallest lower-bound keys, one CTA-wide minimum per round
+        unsigned long long prev = 0ull;
+        for (int r = 0; r < need; ++r) {
+            unsigned long long best = ~0ull;
+            for (int n = tid; n < Nc; n += kMatchThreads) {
+                unsigned long long key;
+                if (lb_key(n, key) && (r == 0 || key > prev) && key < best) best = key;
+            }
+            prev = block_min(best);
+            if (tid == 0) sh.tpick[r] = prev;
+        }
+        __syncthreads();
+        // (b) their exact costs (one warp each) -> U
+        if (warp < need && sh.tpick[warp] != ~0ull) {
+            float iou;
+            const float c = pair_cost(p, b, (int)(sh.tpick[warp] & 0xffffffffu), qx, qy, qw, qh, qc, false, wide, lane,
+                                      sh.terms[warp], &iou);
+            if (lane == 0) sh.tpick[warp] = (unsigned long long)float_ordered(c) << 32;
+        }
+        __syncthreads();
+        unsigned ucut = 0u;
+        for (int r = 0; r < need; ++r)
+            if (sh.tpick[r] != ~0ull) ucut = max(ucut, (unsigned)(sh.tpick[r] >> 32));
+        // (c) windows of the candidate list: exact cost of everything with lb <= U, warp 0 keeps the need smallest keys
+        unsigned long long mine = ~0ull;  // warp 0: lanes 0..need-1 hold the smallest keys so far, ascending
+        for (int w0 = 0; w0 < Nc; w0 += kTinyWindow) {
+            if (tid == 0) sh.tn = 0;
+            __syncthreads();
+            for (int n = w0 + tid; n < min(Nc, w0 + kTinyWindow); n += kMatchThreads) {
+                unsigned long long key;
+                if (lb_key(n, key) && (unsigned)(key >> 32) <= ucut) sh.tlist[atomicAdd(&sh.tn, 1)] = (unsigned short)(n - w0);
+            }
+            __syncthreads();
+            const int tn = sh.tn;
+            for (int t = warp; t < tn; t += kMatchWarps) {
+                const int a = __ldg(ca + w0 + sh.tlist[t]);
+                float iou;
+                const float c = pair_cost(p, b, a, qx, qy, qw, qh, qc, false, wide, lane, sh.terms[warp], &iou);
+                if (lane == 0) sh.tkey[t] = ((unsigned long long)float_ordered(c) << 32) | (unsigned)a;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                for (int t = 0; t < tn; ++t) {
+                    const unsigned long long key = sh.tkey[t];
                     const unsigned long long upk = __shfl_up_sync(0xffffffffu, mine, 1);
                     if (key < mine) mine = (lane == 0 || upk <= key) ? key : upk;
                 }
-                if (lane < need && mine != ~0ull) {
-                    const int a = (int)(mine & 0xffffffffu);
-                    const float iou = pair_iou(gx, gy, gw, gh, load_box(p.preds + ((size_t)b * p.A + a) * p.ch));
-                    if (claim(p, b, a, g, iou)) push_conflict(a);
-                }
             }
         }
+        if (warp == 0 && lane < need && mine != ~0ull) {
+            const int a = (int)(mine & 0xffffffffu);
+            const float iou = pair_iou(qx, qy, qw, qh, load_box(p.preds + ((size_t)b * p.A + a) * p.ch));
+            if (claim(p, b, a, gq, iou)) push_conflict(a);
+        }
+        __syncthreads();
     }
 
     // ---- resolve the conflicts this CTA created (one warp each)
