@@ -46,7 +46,7 @@ struct CandWs {
     int *meta;          // [B, NT*128]  anchor | class << 24
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
     int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | general | tiles done | max x2 | max y2
-    unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | slot
+    unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | anchor
     float4 *gbox;                 // [B, kGroups, kBucketCap]  the same candidates' corners
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
@@ -296,8 +296,9 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     if (pass) {
         int pos = sh.g_base[grp] + __popc(gm & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) pos += sh.g_wcnt[w][grp];
+        // the low bits order equal scores by anchor (ascending anchor == the reference's candidate order)
         const unsigned long long key = ((unsigned long long)cls << 57) |
-                                       ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)islot;
+                                       ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)(tc.anchor_base + src_t);
         if (pos < kBucketCap) {  // a fuller group is redone by the general path from the slot arrays
             p.ws.gkey[((size_t)b * kGroups + grp) * kBucketCap + pos] = key;
             p.ws.gbox[((size_t)b * kGroups + grp) * kBucketCap + pos] = box;
@@ -601,8 +602,7 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
     PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
     // the class-split kernel: class-aware NMS, max_det within its kept-key lists, slots within its key layout
-    const bool split = !class_agnostic && max_det <= kFastMaxDet && (long long)NT * kPpTile <= (1ll << kFastSlotBits) &&
-                       !g_skip_nms;
+    const bool split = !class_agnostic && max_det <= kFastMaxDet && A <= (1 << kFastAnchorBits) && !g_skip_nms;
     const bool pdl = pdl_enabled();
     record_stage_event(1, stream);
     if (g_skip_nms) return PLYOLO_OK;  // debug: time the score stage alone

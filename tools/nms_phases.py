@@ -20,18 +20,20 @@ torch.cuda.synchronize()
 L.plyolo_debug_nms_profile(None)
 p = prof.cpu().numpy().astype(np.int64)
 ws = [w for (k, w) in ops._WS.items() if k[2] == "post"][0]
-ctr = ws[: B * 8 * 4].view(torch.int32).cpu().numpy().reshape(B, 8)
-names = ["wait for tiles", "load + best key", "pre-kill + xcheck", "prefix + scatter", "sort", "sweep", "cluster sync 1",
-         "gather lists + sync 2", "rank + write"]
+ctr = ws[: B * 16 * 4].view(torch.int32).cpu().numpy().reshape(B, 16)
+names = ["wait for tiles", "load + max-first rounds", "survivor histogram", "prefix + scatter", "sort + sweep",
+         "cluster sync 1", "gather lists + sync 2", "rank + write"]
 us = lambda a: a / 1965.0
-done = p[:, 9] > 0
-d = np.diff(p[:, :10], axis=1)[done]
+done = p[:, 8] > 0
+d = np.diff(p[:, :9], axis=1)[done]
 print("phase us over (image, group) CTAs that finished on the fast path (%d of %d): mean / max" % (done.sum(), len(p)))
 for i, n in enumerate(names):
     print("  %-22s %7.2f %7.2f" % (n, us(d[:, i]).mean(), us(d[:, i]).max()))
-work = p[done, 9] - p[done, 1]
+print("  %-22s %7.2f %7.2f" % ("  of which load", us(p[done, 9] - p[done, 1]).mean(), us(p[done, 9] - p[done, 1]).max()))
+print("  %-22s %7.2f %7.2f" % ("  warp 0 in warp_sort", us(p[done, 15]).mean(), us(p[done, 15]).max()))
+work = p[done, 8] - p[done, 1]
 print("  %-22s %7.2f %7.2f" % ("after the tiles", us(work).mean(), us(work).max()))
 print("n per group (max %d)" % p[:, 10].max(), p[:, 10].reshape(B, G)[:8].tolist())
-print("kept per group (max %d), sweep items (max %d), survivors of the pre-kill per group: mean %.0f max %d (of n mean %.0f)" % (p[:, 11].max(), p[:, 13].max(), p[:, 14].mean(), p[:, 14].max(), p[:, 10].mean()))
+print("kept per group (max %d), cross boxes after the filter (max %d), survivors of the rounds per group: mean %.0f max %d (of n mean %.0f)" % (p[:, 11].max(), p[:, 12].max(), p[:, 14].mean(), p[:, 14].max(), p[:, 10].mean()))
 print("ncross", ctr[:, 5].tolist())
 print("general-path flags", ctr[:, 6].tolist(), "tiles done", ctr[:, 7].tolist()[:4])
