@@ -2,8 +2,9 @@
 
 The path shards by image with no data-path collective: every rank decodes / NMSes / assigns its own
 contiguous slice of the batch.  The only exchange is the evaluator's: fixed-size padded detections
-`[B_loc, 300, 6]` + `[B_loc]` counts, all-gathered once (per step or per accumulated chunk) over
-NCCL / NVLink.  The reference has no multi-GPU path at all (train.py:33, devices=1).
+`[B_loc, 300, 6]` + `[B_loc]` counts, all-gathered once per step over NCCL / NVLink — as ONE collective on a
+fused buffer (`fused_det_buffer`), issued on a side stream so that it overlaps the next step's score kernel
+(`DetectionExchange`).  The reference has no multi-GPU path at all (train.py:33, devices=1).
 """
 from __future__ import annotations
 
@@ -62,3 +63,50 @@ def gather_detections(dets: torch.Tensor, counts: torch.Tensor, batch: Optional[
         keep += list(range(r * m, r * m + s))
     idx = torch.tensor(keep, device=dets.device)
     return all_d[idx], all_c[idx]
+
+
+def fused_det_buffer(b_loc: int, max_det: int, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One allocation holding a rank's padded detections and counts back to back, so that ONE collective moves both:
+    -> (buf float32 [b_loc * max_det * 6 + b_loc], dets view [b_loc, max_det, 6], counts int32 view [b_loc])."""
+    n = b_loc * max_det * 6
+    buf = torch.empty(n + b_loc, dtype=torch.float32, device=device)
+    return buf, buf[:n].view(b_loc, max_det, 6), buf[n:].view(torch.int32)
+
+
+def split_gathered(gbuf: torch.Tensor, world: int, b_loc: int, max_det: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Views of an all-gathered fused buffer [world * (b_loc * max_det * 6 + b_loc)] in global image order:
+    -> (dets [world * b_loc, max_det, 6], counts [world * b_loc] int32); copies (ranks are interleaved with counts)."""
+    n = b_loc * max_det * 6
+    g = gbuf.view(world, n + b_loc)
+    return g[:, :n].reshape(world * b_loc, max_det, 6), g[:, n:].contiguous().view(torch.int32).reshape(world * b_loc)
+
+
+class DetectionExchange:
+    """Per-step all-gather of the fused detection buffers, overlapped with the following steps.
+
+    `submit(buf, gbuf)` is called after the step's kernels were enqueued on the current stream: the collective runs on
+    a side stream behind an event, so the next step's score kernel does not wait for it.  A buffer pair may be reused
+    once `wait_for(slot)` was called for it (the compute stream then waits for that slot's collective); `finish()` joins
+    everything back into the current stream."""
+
+    def __init__(self, device, slots: int, group=None):
+        self.side = torch.cuda.Stream(device)
+        self.group = group
+        self.done = [None] * slots
+
+    def wait_for(self, slot: int) -> None:
+        if self.done[slot] is not None:
+            torch.cuda.current_stream().wait_event(self.done[slot])
+
+    def submit(self, slot: int, buf: torch.Tensor, gbuf: torch.Tensor) -> None:
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(gbuf, buf, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[slot] = ev
+
+    def finish(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.side)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pl_yolo_b200.distributed import gather_detections, shard_batch, shard_range
+from pl_yolo_b200.distributed import fused_det_buffer, gather_detections, shard_batch, shard_range, split_gathered
 
 
 def test_shard_range_covers_batch():
@@ -59,3 +59,37 @@ def test_gather_detections_gloo_world2(batch):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _fused_worker(rank, world, port, b_loc, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1)
+        full_d = torch.rand(world * b_loc, 300, 6, generator=g)
+        full_c = torch.randint(0, 301, (world * b_loc,), generator=g, dtype=torch.int32)
+        buf, dets, counts = fused_det_buffer(b_loc, 300, "cpu")
+        dets.copy_(full_d[rank * b_loc:(rank + 1) * b_loc])      # what the C ABI writes through the two views
+        counts.copy_(full_c[rank * b_loc:(rank + 1) * b_loc])
+        gbuf = torch.empty(world * buf.numel())
+        dist.all_gather_into_tensor(gbuf, buf)                    # ONE collective for detections + counts
+        gd, gc = split_gathered(gbuf, world, b_loc, 300)
+        q.put((rank, bool(torch.equal(gd, full_d) and torch.equal(gc, full_c))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_detection_exchange_gloo_world2():
+    """The per-step exchange of bench.py / DESIGN section 7: one all-gather of the fused [dets | counts] buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, port, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
