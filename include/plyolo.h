@@ -51,6 +51,11 @@ extern "C" {
 #define PLYOLO_THR_F64 4      /* fp32 IoU compared against the double threshold (CPU kernel) */
 #define PLYOLO_FLAVOR_CPU 7
 
+/* which reference call site's candidate filter / score / offset arithmetic plyolo_postprocess_yolo_f32 reproduces */
+#define PLYOLO_NMS_YOLOX 0   /* models/evaluators/postprocess.py:7-48 (plyolo_postprocess_f32) */
+#define PLYOLO_NMS_YOLOV3 3  /* models/losses/yolov3/yolov3_decoder.py:72-116 */
+#define PLYOLO_NMS_YOLOV5 5  /* models/losses/yolov5/yolov5_decoder.py:30-87 */
+
 typedef void *plyolo_stream_t; /* cudaStream_t */
 
 int plyolo_version(void);
@@ -93,6 +98,21 @@ int plyolo_postprocess_f32(const float *preds, int B, int A, int C, double conf_
                            int32_t *counts, int32_t *keep_idx, void *workspace, size_t workspace_bytes,
                            plyolo_stream_t stream);
 
+/* The NMS call sites of the sibling heads, multi_label == False:
+ *   PLYOLO_NMS_YOLOV3 (yolov3_decoder.py:72-116): obj > conf, conf = max_c(cls_c * obj) > conf (strict), the max_nms
+ *     best by conf when there are more (:98-100), plain class-agnostic torchvision nms on conf (:103-106: the class
+ *     offset is computed but never applied), rows (x1,y1,x2,y2, obj, conf, class);
+ *   PLYOLO_NMS_YOLOV5 (yolov5_decoder.py:30-87): obj > conf (strict), obj * max_c cls_c >= conf, the max_nms best by
+ *     OBJECTNESS when there are more (:66-67), nms on boxes + class * 4096 (0 if class_agnostic, :70-72) scored by
+ *     objectness, rows (x1,y1,x2,y2, obj, best class score, class).
+ *   preds  [B, N, 5+C] decoded predictions (cx,cy,w,h, obj, cls..), all squashed, as both decoders build them
+ *   dets   [B, max_det, 7] zero padded; counts [B]; keep_idx [B, max_det] row index into preds (-1 padded) or NULL
+ * Limits: min(N, 16384) candidates can be sorted per image; an image with more candidates than that reports
+ * counts[b] = -1 (nothing else is written for it).  Workspace: plyolo_postprocess_workspace_bytes(B, N). */
+int plyolo_postprocess_yolo_f32(const float *preds, int B, int N, int C, double conf_thre, double nms_thre, int variant,
+                                int class_agnostic, int max_nms, int max_det, float *dets, int32_t *counts,
+                                int32_t *keep_idx, void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+
 /* Fused decode + postprocess straight from the head maps (reads them once, never materialises
  * preds): what `postprocess(model(imgs, labels), conf, nms)` computes in validation_step
  * (PL_Modules/pl_detection.py:73-76).  Arguments as the two calls above. */
@@ -122,6 +142,31 @@ int plyolo_simota_f32(const float *preds, const float *labels, int B, int A, int
                       int32_t *matched_gt, float *matched_iou, int32_t *num_fg, int32_t *num_gt,
                       void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The two stand-alone pieces of the assignment that the reference exposes as module-level functions.
+ * plyolo_simota_f32 fuses both with the cost computation; these serve callers of the functions themselves.
+ *
+ * get_in_boxes_info (models/losses/yolox/yolox_loss.py:231-315):
+ *   gt [G,4] (cx,cy,w,h); expanded_strides, x_shifts, y_shifts [A] (the reference's [1,A] tensors)
+ *   fg_mask    [A] uint8     is_in_boxes_or_center (:310)
+ *   in_boxes   [G,A] uint8   is_in_boxes (:276)        in_centers [G,A] uint8  is_in_centers (:306)
+ *   (the reference's second return value is (in_boxes & in_centers)[:, fg_mask], :312-314)
+ *
+ * dynamic_k_matching (:318-370) on a caller-provided cost / IoU matrix:
+ *   cost, ious [G,Nc];  matching [G,Nc] uint8 scratch (the final matching_matrix);  dynamic_ks [G] int32 (:340)
+ *   selected [Nc] uint8 (fg_mask_inboxes, :357), matched_gt [Nc] int32 (-1 if not selected, :363),
+ *   matched_iou [Nc] (:367).  Ties in a cost row go to the lowest index (stable-sort rule).
+ *   exact_k == 0: YOLOX (:342-345: a GT whose k >= Nc - 1 takes every candidate, quirk Q3);
+ *   exact_k != 0: the YOLOv7 matching (models/losses/yolov7/yolov7_loss.py:236-262: torch.topk(cost, k, largest=False),
+ *   exactly k candidates per GT; same conflict rule) on the cost / IoU matrix build_targets computed.
+ * ------------------------------------------------------------------------------------------- */
+int plyolo_in_boxes_info_f32(const float *gt, const float *expanded_strides, const float *x_shifts,
+                             const float *y_shifts, int A, int G, uint8_t *fg_mask, uint8_t *in_boxes,
+                             uint8_t *in_centers, plyolo_stream_t stream);
+int plyolo_dynamic_k_matching_f32(const float *cost, const float *ious, int G, int Nc, int exact_k, uint8_t *matching,
+                                  int32_t *dynamic_ks, uint8_t *selected, int32_t *matched_gt, float *matched_iou,
+                                  plyolo_stream_t stream);
+
 /* pairwise IoU — replaces bboxes_iou (models/layers/losses/iou_loss.py:391-414).
  *   a [na,4], b [nb,4] -> out [na,nb]; xyxy != 0: corner format, else (cx,cy,w,h). */
 int plyolo_bboxes_iou_f32(const float *a, int na, const float *b, int nb, int xyxy, float *out,
@@ -134,6 +179,18 @@ int plyolo_bboxes_iou_f32(const float *a, int na, const float *b, int nb, int xy
  *   out  [B, max_det, 8] rows (x1, y1, x2, y2, w, h, score, class), zero padded past counts[b] */
 int plyolo_format_dets_f32(const float *dets, const int32_t *counts, const float *inv_scales, int B, int max_det,
                            float *out, plyolo_stream_t stream);
+
+/* VOC evaluator statistics on the device — replaces tpfp_default (models/evaluators/eval_voc.py:75-105,
+ * IoU by bbox_overlaps, models/utils/bbox.py:97-139) for every (image, class) of a batch in one launch, instead of the
+ * reference's per-class multiprocessing.Pool(8) over numpy arrays (:18-31).
+ *   dets [B,max_det,6] rows (x1,y1,x2,y2,score,class) in score-descending order per image (what postprocess /
+ *        format_outputs hold), counts [B];  gts [B,Gmax,5] rows (x1,y1,x2,y2,class), gt_counts [B]
+ *   tp   [B,max_det] uint8: 1 = true positive; a valid row with 0 is a false positive (fp = 1 - tp, :81-103)
+ *   num_gts [C] int32: ground-truth boxes per class over the batch (:33-35) — all-reduce it across ranks; the TP flags
+ *        travel with the padded detections in the detection all-gather. */
+int plyolo_voc_tpfp_f32(const float *dets, const int32_t *counts, int B, int max_det, const float *gts,
+                        const int32_t *gt_counts, int Gmax, double iou_thr, int C, uint8_t *tp, int32_t *num_gts,
+                        plyolo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * loss tail of YOLOXLoss (N2) — replaces models/losses/yolox/yolox_loss.py:121-163 for use_l1 == False: the

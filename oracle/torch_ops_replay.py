@@ -176,3 +176,86 @@ def simota(preds: torch.Tensor, labels: torch.Tensor, hw: Sequence[Sequence[int]
         mi_out[b, idx] = (M * ious).sum(0)[sel]                 # :367-369
     return {"fg_mask": fg_out, "matched_gt": mg_out, "matched_iou": mi_out, "num_fg": nfg,
             "num_gt": nlabel.to(torch.int32).cpu(), "dyn_k": dyn, "n_cand": ncand}
+
+
+# ---- sibling heads: the NMS call sites of the YOLOv3 / YOLOv5 decoders and YOLOv7's matching block,
+# replayed op for op on whatever device the inputs live on (multi_label == False, classes == None)
+def yolov3_nms(predictions: torch.Tensor, conf_thre=0.7, nms_thre=0.45, max_nms=10000, max_det=300):
+    """models/losses/yolov3/yolov3_decoder.py:63-116 on the decoded predictions [B,N,5+C] (cx,cy,w,h,obj,cls..)."""
+    predictions = predictions.clone()
+    box_corner = predictions.new(predictions.shape)
+    box_corner[:, :, 0] = predictions[:, :, 0] - predictions[:, :, 2] / 2      # :64-68
+    box_corner[:, :, 1] = predictions[:, :, 1] - predictions[:, :, 3] / 2
+    box_corner[:, :, 2] = predictions[:, :, 0] + predictions[:, :, 2] / 2
+    box_corner[:, :, 3] = predictions[:, :, 1] + predictions[:, :, 3] / 2
+    predictions[:, :, :4] = box_corner[:, :, :4]
+    output = [None for _ in range(len(predictions))]
+    for b_idx, image_pred in enumerate(predictions):
+        image_pred = image_pred[image_pred[..., 4] > conf_thre]                  # :74
+        if not image_pred.size(0):
+            continue
+        image_pred[:, 5:] *= image_pred[:, 4:5]                                  # :79
+        conf, j = image_pred[:, 5:].max(1, keepdim=True)                         # :86
+        x = torch.cat((image_pred[:, :5], conf, j.float()), 1)[conf.view(-1) > conf_thre]
+        n = x.shape[0]
+        if not n:
+            continue
+        elif n > max_nms:
+            x = x[x[:, 5].argsort(descending=True)[:max_nms]]                    # :98-100
+        boxes, scores = x[:, :4], x[:, 5]
+        nms = torchvision.ops.nms(boxes, scores, nms_thre)                       # :106 (class offset never applied)
+        if nms.shape[0] > max_det:
+            nms = nms[:max_det]
+        output[b_idx] = x[nms]
+    return output
+
+
+def yolov5_nms(predictions: torch.Tensor, conf_thre=0.7, nms_thre=0.45, agnostic=False, max_nms=30000, max_det=300):
+    """models/losses/yolov5/yolov5_decoder.py:23-87 on the decoded predictions [B,N,5+C]."""
+    predictions = predictions.clone()
+    obj_mask = predictions[..., 4] > conf_thre                                  # :23
+    max_wh = 4096
+    output = [torch.zeros((0, 7), device=predictions.device)] * predictions.shape[0]
+    for img_idx, x in enumerate(predictions):
+        x = x[obj_mask[img_idx]]
+        if not x.shape[0]:
+            continue
+        box = x[:, :4].clone()                                                   # xywh2xyxy, models/utils/bbox.py:5-12
+        box[:, 0] = x[:, 0] - x[:, 2] / 2
+        box[:, 1] = x[:, 1] - x[:, 3] / 2
+        box[:, 2] = x[:, 0] + x[:, 2] / 2
+        box[:, 3] = x[:, 1] + x[:, 3] / 2
+        x[:, :4] = box
+        obj = x[:, 4]
+        conf, j = x[:, 5:].max(1, keepdim=True)                                  # :57
+        conf_mask = ((obj[:, None] * conf) >= conf_thre).squeeze(-1)             # :58
+        x = torch.cat((box, obj[:, None], conf, j.float()), 1)[conf_mask]
+        n = x.shape[0]
+        if not n:
+            continue
+        elif n > max_nms:
+            x = x[x[:, 4].argsort(descending=True)[:max_nms]]                    # :66-67
+        c = x[:, 6] * (0 if agnostic else max_wh)                                # :70
+        boxes, scores = x[:, :4] + c.unsqueeze(-1), x[:, 4]                      # :71
+        i = torchvision.ops.nms(boxes, scores, nms_thre)                         # :72
+        if i.shape[0] > max_det:
+            i = i[:max_det]
+        output[img_idx] = x[i]
+    return output
+
+
+def yolov7_matching(cost: torch.Tensor, pair_wise_iou: torch.Tensor):
+    """models/losses/yolov7/yolov7_loss.py:233-262 -> (fg_mask_inboxes [N] bool, matched_gt_inds, dynamic_ks)."""
+    top_k, _ = torch.topk(pair_wise_iou, min(10, pair_wise_iou.shape[1]), dim=1)   # :233
+    dynamic_ks = torch.clamp(top_k.sum(1).int(), min=1)                            # :234
+    matching_matrix = torch.zeros_like(cost)
+    for gt_idx in range(cost.shape[0]):
+        _, pos_idx = torch.topk(cost[gt_idx], k=dynamic_ks[gt_idx].item(), largest=False)   # :243-246
+        matching_matrix[gt_idx][pos_idx] = 1.0
+    anchor_matching_gt = matching_matrix.sum(0)
+    if (anchor_matching_gt > 1).sum() > 0:                                         # :251-254
+        _, cost_argmin = torch.min(cost[:, anchor_matching_gt > 1], dim=0)
+        matching_matrix[:, anchor_matching_gt > 1] *= 0.0
+        matching_matrix[cost_argmin, anchor_matching_gt > 1] = 1.0
+    fg_mask_inboxes = matching_matrix.sum(0) > 0.0
+    return fg_mask_inboxes, matching_matrix[:, fg_mask_inboxes].argmax(0), dynamic_ks

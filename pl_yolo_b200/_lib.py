@@ -12,6 +12,7 @@ SO_PATH = os.path.join(_HERE, "libplyolo.so")
 
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 FLAVOR_CUDA, NMS_RULE_CPU, IOU_NOFMA, THR_F64, FLAVOR_CPU = 0, 1, 2, 4, 7
+NMS_YOLOX, NMS_YOLOV3, NMS_YOLOV5 = 0, 3, 5
 MAX_LEVELS = 8
 
 _lib = None
@@ -34,6 +35,9 @@ def _declare(lib):
     lib.plyolo_postprocess_f32.restype = c_int
     lib.plyolo_postprocess_f32.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_int,
                                            vp, vp, vp, vp, c_size_t, vp]
+    lib.plyolo_postprocess_yolo_f32.restype = c_int
+    lib.plyolo_postprocess_yolo_f32.argtypes = [vp, c_int, c_int, c_int, c_double, c_double, c_int, c_int, c_int, c_int,
+                                                vp, vp, vp, vp, c_size_t, vp]
     lib.plyolo_decode_postprocess_f32.restype = c_int
     lib.plyolo_decode_postprocess_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, c_double,
                                                   c_double, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
@@ -42,6 +46,12 @@ def _declare(lib):
     lib.plyolo_simota_f32.restype = c_int
     lib.plyolo_simota_f32.argtypes = [vp, vp, c_int, c_int, c_int, c_int, ip, ip, ip, c_int, vp, vp, vp, vp, vp, vp,
                                       c_size_t, vp]
+    lib.plyolo_in_boxes_info_f32.restype = c_int
+    lib.plyolo_in_boxes_info_f32.argtypes = [vp, vp, vp, vp, c_int, c_int, vp, vp, vp, vp]
+    lib.plyolo_dynamic_k_matching_f32.restype = c_int
+    lib.plyolo_dynamic_k_matching_f32.argtypes = [vp, vp, c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]
+    lib.plyolo_voc_tpfp_f32.restype = c_int
+    lib.plyolo_voc_tpfp_f32.argtypes = [vp, vp, c_int, c_int, vp, vp, c_int, c_double, c_int, vp, vp, vp]
     lib.plyolo_format_dets_f32.restype = c_int
     lib.plyolo_format_dets_f32.argtypes = [vp, vp, vp, c_int, c_int, vp, vp]
     lib.plyolo_bboxes_iou_f32.restype = c_int

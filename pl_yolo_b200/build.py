@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libplyolo.so")
-SOURCES = ["api.cu", "decode.cu", "postprocess.cu", "simota.cu", "loss.cu"]
+SOURCES = ["api.cu", "decode.cu", "postprocess.cu", "simota.cu", "simota_ops.cu", "loss.cu", "evaluator.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "static",

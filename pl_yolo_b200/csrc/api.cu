@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace plyolo {
@@ -72,6 +74,19 @@ int make_levels(Levels &lv, const float *const *host_lvl, const int *hs, const i
     return PLYOLO_OK;
 }
 
+}  // namespace plyolo
+
+namespace plyolo {
+bool first_use_on_device(int tag) {
+    static std::mutex mu;
+    static bool done[8][64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (tag < 0 || tag >= 8 || done[tag][dev]) return false;
+    done[tag][dev] = true;
+    return true;
+}
 }  // namespace plyolo
 
 extern "C" {

@@ -56,6 +56,10 @@ int make_levels(Levels &lv, const float *const *host_lvl, const int *hs, const i
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// true exactly once per (call site tag, current device): kernel attributes are per device and are set to fixed maxima,
+// so no launch ever changes what another host thread relies on (api.cu)
+bool first_use_on_device(int tag);
+
 // ---- device side ---------------------------------------------------------------------------
 // sigmoid exactly as ATen's CUDA kernel: 1 / (1 + exp(-x)) (bit-equal on B200, tools/probe_aten_cuda.py)
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }

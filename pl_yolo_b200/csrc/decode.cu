@@ -127,11 +127,7 @@ extern "C" int plyolo_decode_f32(const float *const *host_lvl, const int *hs, co
     for (int l = 0; l < p.lv.n; ++l) vec = vec && (p.lv.hw[l] & 3) == 0;
     p.vec_ok = vec ? 1 : 0;
     const size_t smem = (size_t)kDecTile * p.ch * sizeof(float);
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
-    }
+    if (first_use_on_device(0)) cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     dim3 grid(p.lv.tile0[p.lv.n], B);
     decode_kernel<<<grid, kDecThreads, smem, (cudaStream_t)stream>>>(p);
     PLYOLO_CHECK_LAUNCH("decode_kernel");

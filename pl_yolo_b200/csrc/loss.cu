@@ -314,11 +314,7 @@ extern "C" int plyolo_yolox_loss_backward_f32(const float *preds, const float *l
     for (int l = 0; l < p.lv.n; ++l) vec = vec && ((uintptr_t)p.lv.ptr[l] & 15) == 0 && (p.lv.hw[l] & 3) == 0;
     p.vec_ok = vec ? 1 : 0;
     const size_t smem = (size_t)kLossTile * p.f.ch * sizeof(float);
-    static thread_local bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(yolox_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
-    }
+    if (first_use_on_device(1)) cudaFuncSetAttribute(yolox_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     yolox_loss_bwd_kernel<<<dim3(p.lv.tile0[p.lv.n], B), kLossThreads, smem, (cudaStream_t)stream>>>(p);
     PLYOLO_CHECK_LAUNCH("yolox_loss_bwd_kernel");
     return PLYOLO_OK;

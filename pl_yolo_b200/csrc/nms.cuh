@@ -105,6 +105,8 @@ __host__ __device__ inline size_t nms_smem_bytes(const int sort_cap, const int f
 
 struct NmsParams {
     int B, NT, max_nms, max_det, flavor, agnostic, sort_cap, fast_cap;
+    int variant;      // PLYOLO_NMS_*: 0 = postprocess.py / batched_nms; YOLOv3 / YOLOv5 decoder call sites otherwise (general path only)
+    float fixed_span; // > 0: class offset = class * fixed_span (yolov5_decoder.py:70) instead of max_coordinate + 1
     int all_general;  // nms_general_kernel: every image takes the general path (no class-split kernel ran)
     int wait_tiles;   // nms_fast_kernel: spin on the image's scored-tile counter (the score kernel may still be running)
     float thr_f;
@@ -378,6 +380,28 @@ __device__ __forceinline__ void warp_class_nms(const unsigned long long *keys, c
 template <typename SlotOf>
 __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, const size_t slot0, const int nkept,
                                            SlotOf slot_of) {
+    if (p.variant != PLYOLO_NMS_YOLOX) {
+        // sibling decoders: rows (x1,y1,x2,y2, obj, conf / best class score, class) — yolov3_decoder.py:88, yolov5_decoder.py:59
+        for (int i = threadIdx.x; i < p.max_det; i += kNmsThreads) {
+            float *d = p.dets + ((size_t)b * p.max_det + i) * 7;
+            if (i < nkept) {
+                const int slot = slot_of(i);
+                const float4 bx = p.ws.box[slot0 + slot];
+                const int meta = p.ws.meta[slot0 + slot];
+                const float sc = p.ws.score[slot0 + slot], ax = p.ws.aux[slot0 + slot];
+                d[0] = bx.x; d[1] = bx.y; d[2] = bx.z; d[3] = bx.w;
+                d[4] = p.variant == PLYOLO_NMS_YOLOV3 ? ax : sc;   // objectness
+                d[5] = p.variant == PLYOLO_NMS_YOLOV3 ? sc : ax;   // conf (v3) / best class score (v5)
+                d[6] = (float)(meta >> 24);
+                if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = meta & 0xffffff;
+            } else {
+                for (int q = 0; q < 7; ++q) d[q] = 0.f;
+                if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
+            }
+        }
+        if (threadIdx.x == 0) p.counts[b] = nkept;
+        return;
+    }
     for (int i = threadIdx.x; i < p.max_det; i += kNmsThreads) {
         float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
         if (i < nkept) {
@@ -440,13 +464,21 @@ __device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned
     }
     if (tid < kMaxClasses) cls_cnt[tid] = 0;
     __syncthreads();
-    const int Nk = min(s_total, p.max_nms);  // postprocess.py:24-25 — first max_nms in anchor order
+    // postprocess.py:24-25 keeps the first max_nms candidates in anchor order; the YOLOv3 / YOLOv5 decoders keep the
+    // max_nms BEST ones (argsort, yolov3_decoder.py:98-100, yolov5_decoder.py:66-67): all candidates are sorted and the
+    // sweep stops after max_nms of them
+    const bool by_score = p.variant != PLYOLO_NMS_YOLOX;
+    const int Nk = by_score ? s_total : min(s_total, p.max_nms);
+    if (Nk > p.sort_cap) {  // (sibling call sites only) more candidates than one CTA can sort: reported, not guessed
+        if (tid == 0) p.counts[b] = -1;
+        return;
+    }
     NMS_PROF(1);
 
-    // batched_nms branch (tv:ops/boxes.py:80): per-class loop vs coordinate trick
-    const bool per_class = !p.agnostic && 4 * (long long)Nk > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
+    // batched_nms branch (tv:ops/boxes.py:80): per-class loop vs coordinate trick; the sibling decoders call plain nms
+    const bool per_class = !by_score && !p.agnostic && 4 * (long long)Nk > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);
     const bool use_off = !p.agnostic && !per_class;
-    bool fast = !p.agnostic && Nk <= p.fast_cap;
+    bool fast = !by_score && !p.agnostic && Nk <= p.fast_cap;
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(kept_fast);  // fast path: keys in candidate order
 
     // ---- one pass over the candidates (rank r = position in anchor order): key, max coordinate
@@ -490,9 +522,11 @@ __device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned
         for (int w = 1; w < kNmsWarps; ++w) mx = fmaxf(mx, red[w]);
         return mx;
     };
-    float span = build_keys(fast, fast ? stage : keys) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
-    // the same-class shortcut needs offsets that dwarf their own rounding error (ulp(C*span) << 0.5)
-    const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
+    const float max_coord1 = build_keys(fast, fast ? stage : keys) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
+    const float span = p.fixed_span > 0.f ? p.fixed_span : max_coord1;       // yolov5_decoder.py:70: class * 4096
+    // the same-class shortcut needs offsets that dwarf their own rounding error (ulp(C*span) << 0.5) and class ranges
+    // wide enough for every box (always true for max_coordinate + 1)
+    const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f && max_coord1 <= span;
     NMS_PROF(2);
 
     if (fast && (!use_off || filter_ok) && s_ncross <= kMaxCross) {
@@ -641,6 +675,7 @@ __device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned
     for (int i = Nk + tid; i < n_pad; i += kNmsThreads) keys[i] = ~0ull;
     __syncthreads();
     block_sort(keys, n_pad);
+    const int Nlim = by_score ? min(Nk, p.max_nms) : Nk;  // score-sorted truncation of the sibling call sites
 
     float4 *kept_box = reinterpret_cast<float4 *>(region);                 // [max_det]
     float4 *cbox = kept_box + p.max_det;                                   // [kRound]
@@ -656,10 +691,10 @@ __device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned
     //       build the suppression bit-matrix among survivors only;
     //   (C) warp 0 sweeps the survivors sequentially over the remaining bits (ffs), appends the keeps,
     // and the loop exits as soon as max_det boxes are kept (output order == score order == sweep order).
-    for (int base = 0; base < Nk; base += kRound) {
+    for (int base = 0; base < Nlim; base += kRound) {
         const int nkept = s_nkept;
         if (nkept >= p.max_det) break;
-        const int nch = min(kRound, Nk - base);
+        const int nch = min(kRound, Nlim - base);
         const int ci = tid / kSub, sub = tid % kSub;
         // (A) every thread of a candidate fetches the same record (one broadcast request per candidate)
         bool sup = false;

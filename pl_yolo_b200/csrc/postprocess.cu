@@ -44,6 +44,7 @@ struct CandWs {
     float4 *box;        // [B, NT*128]  original (un-offset) corners
     float *score;       // [B, NT*128]
     int *meta;          // [B, NT*128]  anchor | class << 24
+    float *aux;         // [B, NT*128]  second score of the YOLOv3 / YOLOv5 call sites (objectness / best class score)
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
     int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | general | tiles done | max x2 | max y2
     unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | anchor
@@ -58,6 +59,7 @@ struct ScoreParams {
     int B, A, C, ch, NT;
     float conf_thr;
     int bulk_ok;
+    int variant;  // PLYOLO_NMS_YOLOX / _YOLOV3 / _YOLOV5: which reference call site's filter + score arithmetic (preds input only)
     CandWs ws;
     long long *prof;  // debug: [gridDim.x][kConsumers][8] accumulated cycles per consumer phase, or null
 };
@@ -126,7 +128,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     const int ch = p.ch, b = tc.b, l = tc.l, a0 = tc.a0, cnt = tc.cnt;
     const int lane = tid & 31, warp = tid >> 5;
     bool pass = false;
-    float conf = 0.f;
+    float conf = 0.f, aux = 0.f;
     int cls = 0;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     const int src_t = tid;  // tile-local anchor of this thread
@@ -224,14 +226,42 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         }
     } else if (tid < cnt) {
         const float *r = tile + tid * ch;
-        float best = r[5];
-        for (int c = 1; c < p.C; ++c) {
-            const float s = r[5 + c];
-            if (s > best) { best = s; cls = c; }  // postprocess.py:18, first max index
+        if (p.variant == PLYOLO_NMS_YOLOX) {
+            float best = r[5];
+            for (int c = 1; c < p.C; ++c) {
+                const float s = r[5 + c];
+                if (s > best) { best = s; cls = c; }  // postprocess.py:18, first max index
+            }
+            conf = r[4] * best;
+            pass = conf >= p.conf_thr;
+            box = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+            // YOLOv3 / YOLOv5 decoders: rows are (cx, cy, w, h, obj, cls..) already squashed
+            const float obj = r[4];
+            if (obj > p.conf_thr) {  // yolov3_decoder.py:74, yolov5_decoder.py:23 (strict)
+                if (p.variant == PLYOLO_NMS_YOLOV3) {
+                    float best = r[5] * obj;  // :79 cls *= obj, :86 max over the products (first max index)
+                    for (int c = 1; c < p.C; ++c) {
+                        const float s = r[5 + c] * obj;
+                        if (s > best) { best = s; cls = c; }
+                    }
+                    conf = best;               // the NMS score (:104)
+                    aux = obj;
+                    pass = conf > p.conf_thr;  // :87 (strict)
+                } else {
+                    float best = r[5];         // yolov5_decoder.py:57 max over the raw class scores
+                    for (int c = 1; c < p.C; ++c) {
+                        const float s = r[5 + c];
+                        if (s > best) { best = s; cls = c; }
+                    }
+                    pass = (obj * best) >= p.conf_thr;  // :58
+                    conf = obj;                // the NMS score is the objectness (:71)
+                    aux = best;
+                }
+                // box_corner (yolov3_decoder.py:64-68) / xywh2xyxy (models/utils/bbox.py:5-12)
+                box = make_float4(r[0] - r[2] / 2, r[1] - r[3] / 2, r[0] + r[2] / 2, r[1] + r[3] / 2);
+            }
         }
-        conf = r[4] * best;
-        pass = conf >= p.conf_thr;
-        box = make_float4(r[0], r[1], r[2], r[3]);
     }
     TPROF(2);
     release();  // last read of the tile is done (every thread calls it)
@@ -272,6 +302,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         p.ws.box[slot] = box;
         p.ws.score[slot] = conf;
         p.ws.meta[slot] = (tc.anchor_base + src_t) | (cls << 24);
+        if (!FUSED && p.variant != PLYOLO_NMS_YOLOX) p.ws.aux[slot] = aux;
     }
     if (tid == 0) p.ws.tile_count[b * p.NT + tc.tile_id] = total;
 
@@ -497,6 +528,7 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t o_box = take(slots * sizeof(float4));
     size_t o_sc = take(slots * sizeof(float));
     size_t o_meta = take(slots * sizeof(int));
+    size_t o_aux = take(slots * sizeof(float));
     size_t o_gkey = take((size_t)B * kGroups * kBucketCap * sizeof(unsigned long long));
     size_t o_gbox = take((size_t)B * kGroups * kBucketCap * sizeof(float4));
     size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
@@ -507,6 +539,7 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
         ws->box = reinterpret_cast<float4 *>(base + o_box);
         ws->score = reinterpret_cast<float *>(base + o_sc);
         ws->meta = reinterpret_cast<int *>(base + o_meta);
+        ws->aux = reinterpret_cast<float *>(base + o_aux);
         ws->gkey = reinterpret_cast<unsigned long long *>(base + o_gkey);
         ws->gbox = reinterpret_cast<float4 *>(base + o_gbox);
         ws->xkey = reinterpret_cast<unsigned long long *>(base + o_xkey);
@@ -587,13 +620,17 @@ static cudaError_t launch_ex(void (*kernel)(Args...), dim3 grid, dim3 block, siz
 // `overlap`: the score stage was the persistent kernel (it triggers its dependents at once and publishes the
 // per-image scored-tile counters), so the class-split NMS may start under it.
 static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
-                   const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream) {
+                   const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream,
+                   int variant = PLYOLO_NMS_YOLOX) {
     NmsParams np;
     np.B = B; np.NT = NT; np.max_nms = max_nms; np.max_det = max_det; np.flavor = flavor;
+    np.variant = variant;
+    np.fixed_span = variant == PLYOLO_NMS_YOLOV5 ? 4096.f : 0.f;             // yolov5_decoder.py:27, :70
+    if (variant == PLYOLO_NMS_YOLOV3) class_agnostic = 1;                     // yolov3_decoder.py:103-106: offset never applied
     np.agnostic = class_agnostic ? 1 : 0;
     np.thr_f = (float)nms_thre; np.thr_d = nms_thre;
     int cap = 64;
-    const int need = max_nms < A ? max_nms : A;
+    const int need = variant != PLYOLO_NMS_YOLOX ? (A < kMaxSortCap ? A : kMaxSortCap) : (max_nms < A ? max_nms : A);
     while (cap < need) cap <<= 1;
     np.sort_cap = cap;
     np.fast_cap = cap < kFastCap ? cap : kFastCap;
@@ -602,7 +639,8 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
     PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
     // the class-split kernel: class-aware NMS, max_det within its kept-key lists, slots within its key layout
-    const bool split = !class_agnostic && max_det <= kFastMaxDet && A <= (1 << kFastAnchorBits) && !g_skip_nms;
+    const bool split = variant == PLYOLO_NMS_YOLOX && !class_agnostic && max_det <= kFastMaxDet && A <= (1 << kFastAnchorBits) &&
+                       !g_skip_nms;
     const bool pdl = pdl_enabled();
     record_stage_event(1, stream);
     if (g_skip_nms) return PLYOLO_OK;  // debug: time the score stage alone
@@ -739,6 +777,7 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.conf_thr = (float)conf_thre;  // `tensor >= python float` compares in fp32
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (A & 3) == 0) ? 1 : 0;
     sp.prof = nullptr;
+    sp.variant = PLYOLO_NMS_YOLOX;
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
@@ -769,10 +808,38 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     for (int l = 0; l < sp.lv.n; ++l) bulk = bulk && ((uintptr_t)sp.lv.ptr[l] & 15) == 0 && (sp.lv.hw[l] & 3) == 0;
     sp.bulk_ok = bulk ? 1 : 0;
     sp.prof = g_score_prof;
+    sp.variant = PLYOLO_NMS_YOLOX;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<true>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
                    overlap, (cudaStream_t)stream);
+}
+
+extern "C" int plyolo_postprocess_yolo_f32(const float *preds, int B, int N, int C, double conf_thre, double nms_thre,
+                                           int variant, int class_agnostic, int max_nms, int max_det, float *dets,
+                                           int32_t *counts, int32_t *keep_idx, void *workspace, size_t workspace_bytes,
+                                           plyolo_stream_t stream) {
+    using namespace plyolo;
+    PLYOLO_REQUIRE(preds != nullptr, "preds is null");
+    PLYOLO_REQUIRE(variant == PLYOLO_NMS_YOLOV3 || variant == PLYOLO_NMS_YOLOV5, "variant=%d is not a YOLOv3 / YOLOv5 call site", variant);
+    int rc = check_post_args(B, N, C, max_nms < kMaxSortCap ? max_nms : kMaxSortCap, max_det, 0, dets, counts, workspace, workspace_bytes);
+    if (rc != PLYOLO_OK) return rc;
+    rc = check_device();
+    if (rc != PLYOLO_OK) return rc;
+    ScoreParams sp;
+    sp.preds = preds; sp.B = B; sp.A = N; sp.C = C; sp.ch = 5 + C;
+    sp.NT = (N + kPpTile - 1) / kPpTile;
+    sp.conf_thr = (float)conf_thre;  // `tensor > python float` compares in fp32
+    sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (N & 3) == 0) ? 1 : 0;
+    sp.prof = nullptr;
+    sp.variant = variant;
+    sp.lv.n = 0; sp.lv.A = N;
+    cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
+    bool overlap = false;
+    rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
+    if (rc != PLYOLO_OK) return rc;
+    return run_nms(B, N, sp.NT, nms_thre, class_agnostic, max_nms, max_det, 0, sp.ws, dets, counts, keep_idx, overlap,
+                   (cudaStream_t)stream, variant);
 }

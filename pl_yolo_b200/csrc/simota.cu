@@ -995,6 +995,7 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
                 best = other < best ? other : best;
             }
+            __syncwarp();  // every lane has read the states of this round
             if (lane == 0) {
                 const int i = (int)(best & 0xffffffffu);
                 sh.state[gi][i] = 1;
@@ -1318,14 +1319,16 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bm = (2 * (size_t)((A + 31) / 32) + 1 + (size_t)(A / kPrepSplit + 128) + (size_t)Lmax) * sizeof(unsigned);
     PLYOLO_REQUIRE(bm <= 160 * 1024, "A=%d too large for the candidate bitmap", A);
-    if (bm > 40 * 1024) cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm);
+    if (first_use_on_device(2)) {  // fixed maxima, once per device
+        cudaFuncSetAttribute(simota_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));
+    }
     record_stage_event(0, st);
     simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
     simota_sweep_kernel<<<dim3((Lmax + kSweepGts - 1) / kSweepGts, B), kSweepThreads, 0, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_sweep_kernel");
     record_stage_event(1, st);
-    cudaFuncSetAttribute(simota_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchShared));
     simota_match_kernel<<<dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), kMatchThreads, sizeof(MatchShared), st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_match_kernel");
     record_stage_event(2, st);

@@ -131,6 +131,29 @@ def _(preds, conf_thre, nms_thre, class_agnostic, max_nms, max_det, flavor):
             preds.new_empty((B, max_det), dtype=torch.int32))
 
 
+def postprocess_yolo_raw(preds: torch.Tensor, conf_thre: float, nms_thre: float, variant: int, class_agnostic: bool, max_nms: int,
+                         max_det: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """NMS call sites of the YOLOv3 / YOLOv5 decoders on decoded predictions [B,N,5+C] (cx,cy,w,h,obj,cls..):
+    -> (dets [B,max_det,7] rows (x1,y1,x2,y2,obj,conf,class) zero padded, counts [B] i32 (-1: more candidates than the
+    kernel sorts), keep_idx [B,max_det] i32)."""
+    p = _check_cuda_f32(preds, "predictions")
+    if p.dim() != 3 or p.shape[2] < 6:
+        raise ValueError("predictions must be [B, N, 5+C]")
+    B, N, ch = p.shape
+    dev = p.device
+    dets = torch.empty((B, max_det, 7), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _workspace("post", L.plyolo_postprocess_workspace_bytes(B, N), dev)
+        rc = L.plyolo_postprocess_yolo_f32(p.data_ptr(), B, N, ch - 5, float(conf_thre), float(nms_thre), int(variant),
+                                           int(class_agnostic), int(max_nms), int(max_det), dets.data_ptr(), counts.data_ptr(),
+                                           keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_postprocess_yolo_f32")
+    return dets, counts, keep
+
+
 def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_thre: float, nms_thre: float,
                            class_agnostic: bool, max_nms: int, max_det: int, flavor: int,
                            out=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -210,6 +233,50 @@ def _(preds, labels, hw, strides):
     B, A = preds.shape[0], preds.shape[1]
     return (preds.new_empty((B, A), dtype=torch.bool), preds.new_empty((B, A), dtype=torch.int32),
             preds.new_empty((B, A)), preds.new_empty((B,), dtype=torch.int32), preds.new_empty((B,), dtype=torch.int32))
+
+
+def in_boxes_info_raw(gt: torch.Tensor, expanded_strides: torch.Tensor, x_shifts: torch.Tensor,
+                      y_shifts: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """get_in_boxes_info (yolox_loss.py:231-315): gt [G,4], the three [A] (or [1,A]) anchor vectors
+    -> (fg_mask [A] bool, in_boxes [G,A] bool, in_centers [G,A] bool)."""
+    g = _check_cuda_f32(gt, "gt_bboxes_per_image")
+    es = _check_cuda_f32(expanded_strides, "expanded_strides").reshape(-1)
+    xs = _check_cuda_f32(x_shifts, "x_shifts").reshape(-1)
+    ys = _check_cuda_f32(y_shifts, "y_shifts").reshape(-1)
+    if g.dim() != 2 or g.shape[1] != 4 or not (es.numel() == xs.numel() == ys.numel()):
+        raise ValueError("gt must be [G,4] and the anchor vectors must have one length")
+    A, G = es.numel(), g.shape[0]
+    dev = g.device
+    fg = torch.empty((A,), dtype=torch.uint8, device=dev)
+    ib = torch.empty((G, A), dtype=torch.uint8, device=dev)
+    ic = torch.empty((G, A), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().plyolo_in_boxes_info_f32(g.data_ptr(), es.data_ptr(), xs.data_ptr(), ys.data_ptr(), A, G, fg.data_ptr(),
+                                                 ib.data_ptr(), ic.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_in_boxes_info_f32")
+    return fg.view(torch.bool), ib.view(torch.bool), ic.view(torch.bool)
+
+
+def dynamic_k_matching_raw(cost: torch.Tensor, ious: torch.Tensor, exact_k: bool = False):
+    """dynamic_k_matching (yolox_loss.py:318-370) on a [G,Nc] cost / IoU matrix -> (selected [Nc] bool,
+    matched_gt [Nc] i32 (-1 = not selected), matched_iou [Nc], dynamic_ks [G] i32, matching [G,Nc] bool).
+    exact_k: the YOLOv7 rule (yolov7_loss.py:236-262, torch.topk: exactly k per GT, no `k >= Nc-1` quirk)."""
+    c = _check_cuda_f32(cost, "cost")
+    i = _check_cuda_f32(ious, "pair_wise_ious")
+    if c.dim() != 2 or c.shape != i.shape:
+        raise ValueError("cost and pair_wise_ious must be [G,Nc]")
+    G, Nc = c.shape
+    dev = c.device
+    M = torch.empty((G, Nc), dtype=torch.uint8, device=dev)
+    dk = torch.empty((G,), dtype=torch.int32, device=dev)
+    sel = torch.zeros((Nc,), dtype=torch.uint8, device=dev)
+    mg = torch.full((Nc,), -1, dtype=torch.int32, device=dev)
+    mi = torch.zeros((Nc,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().plyolo_dynamic_k_matching_f32(c.data_ptr(), i.data_ptr(), G, Nc, int(exact_k), M.data_ptr(), dk.data_ptr(),
+                                                      sel.data_ptr(), mg.data_ptr(), mi.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_dynamic_k_matching_f32")
+    return sel.view(torch.bool), mg, mi, dk, M.view(torch.bool)
 
 
 # ------------------------------------------------------------------------------------------ loss tail (N2)

@@ -43,10 +43,16 @@ class LazyPredictions:
     def __getitem__(self, idx):
         return self.tensor[idx]
 
-    def __torch_function__(self, func, types, args=(), kwargs=None):  # pragma: no cover - convenience only
-        kwargs = kwargs or {}
-        args = [a.tensor if isinstance(a, LazyPredictions) else a for a in args]
-        return func(*args, **kwargs)
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        """torch functions applied to the lazy object see the materialised reference tensor."""
+        def unwrap(a):
+            if isinstance(a, LazyPredictions):
+                return a.tensor
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(x) for x in a)
+            return a
+        return func(*unwrap(tuple(args)), **{k: unwrap(v) for k, v in (kwargs or {}).items()})
 
 
 def postprocess_dense(predictions: Union[torch.Tensor, LazyPredictions], conf_thre: float = 0.7, nms_thre: float = 0.45,
@@ -93,8 +99,19 @@ def format_outputs(outputs, ids, hws, val_size, class_ids, labels=None):
     det_list = [[np.empty(shape=[0, 5]) for _ in range(len(class_ids))] for _ in range(n_img)]
     if n_img == 0:
         return json_list, det_list
+    # like the reference's zip(outputs, hws[0], hws[1], ids), the shortest argument decides how many images are visited
+    n_img = min(n_img, len(hws[0]), len(hws[1]), len(ids))
     dense = getattr(outputs, "dense", None)
-    if dense is None:  # a plain list (e.g. produced elsewhere): pad it to the dense layout first
+    if dense is not None:
+        # the cached batch result is only valid while every entry still is the view `postprocess` returned
+        d0, cnt0 = dense[0], outputs.counts_host
+        same = len(cnt0) == len(outputs) and all(
+            (o is None and cnt0[i] == 0) or (o is not None and cnt0[i] == o.shape[0] and o.data_ptr() == d0[i].data_ptr())
+            for i, o in enumerate(outputs))
+        if not same:
+            dense = None
+    outputs = list(outputs)[:n_img] if dense is None else outputs
+    if dense is None:  # a plain list (e.g. produced elsewhere, or edited since): pad it to the dense layout first
         first = next((o for o in outputs if o is not None), None)
         if first is None:
             return json_list, det_list
@@ -107,13 +124,15 @@ def format_outputs(outputs, ids, hws, val_size, class_ids, labels=None):
         counts = torch.tensor(cnt, dtype=torch.int32, device=dets.device)
     else:
         (dets, counts), cnt = dense, outputs.counts_host
+        if n_img < dets.shape[0]:
+            dets, counts, cnt = dets[:n_img], counts[:n_img].contiguous(), cnt[:n_img]
     # scale = min(val_size[0] / float(img_w), val_size[1] / float(img_h)) in Python doubles (postprocess.py:111)
     scales = [min(val_size[0] / float(w), val_size[1] / float(h)) for h, w in zip(hws[0], hws[1])][:n_img]
     # `tensor /= python_float` on CUDA multiplies by the reciprocal taken in double and rounded to fp32
     sc = torch.tensor([1.0 / v for v in scales], dtype=torch.float64).to(torch.float32).to(dets.device)
     rows = ops.format_dets_raw(dets, counts, sc)
     # the reference's in-place `bboxes /= scale` is visible to the caller through `outputs`
-    for i, o in enumerate(outputs):
+    for i, o in zip(range(n_img), outputs):
         if o is not None:
             o[:, 0:4] = rows[i, : cnt[i], 0:4]
     host = rows.cpu().numpy()  # the one device->host copy

@@ -64,6 +64,8 @@ class _FusedTrainLoss(torch.autograd.Function):
         for x in inputs:
             hw += [int(x.shape[2]), int(x.shape[3])]
         labels = labels.to(preds.dtype).contiguous()
+        if labels.shape[1] == 0:  # no label rows at all: the reference returns the objectness-only loss (:57-62)
+            labels = labels.new_zeros((labels.shape[0], 1, 5))
         fg, mg, miou, nfg, ngt = ops.simota_assign_raw(preds, labels, hw, strides)
         sums = ops.yolox_loss_sums_raw(preds, labels, fg, mg, miou)
         ctx.strides, ctx.hw = strides, hw
@@ -186,3 +188,25 @@ class YOLOXLoss(nn.Module):
         loss = 5.0 * loss_iou + loss_obj + loss_cls + loss_l1      # :162-163
         return {"loss": loss, "loss_iou": loss_iou, "loss_obj": loss_obj, "loss_cls": loss_cls, "loss_l1": loss_l1,
                 "proportion": num_fgs / max(num_gts, 1)}
+
+
+def get_in_boxes_info(gt_bboxes_per_image, expanded_strides, x_shifts, y_shifts, total_num_anchors, num_gt):
+    """Drop-in for the module-level function of models/losses/yolox/yolox_loss.py:231-315 (same arguments):
+    -> (is_in_boxes_or_center [A] bool, is_in_boxes_and_center [num_gt, Nc] bool)."""
+    fg, in_boxes, in_centers = ops.in_boxes_info_raw(gt_bboxes_per_image[:num_gt].contiguous(), expanded_strides, x_shifts, y_shifts)
+    if fg.numel() != total_num_anchors:
+        raise ValueError("total_num_anchors does not match the anchor vectors")
+    return fg, in_boxes[:, fg] & in_centers[:, fg]                                    # :312-314
+
+
+def dynamic_k_matching(fg_mask, cost, pair_wise_ious, gt_classes, num_gt):
+    """Drop-in for models/losses/yolox/yolox_loss.py:318-370 (same arguments and return values; `fg_mask` is updated
+    in place like the reference does, :361): -> (fg_mask, num_fg, matched_gt_inds, gt_matched_classes,
+    pred_ious_this_matching)."""
+    sel, mg, mi, _, _ = ops.dynamic_k_matching_raw(cost[:num_gt], pair_wise_ious[:num_gt])
+    num_fg = sel.sum().detach()                                                       # :358
+    fg_mask[fg_mask.clone()] = sel                                                    # :361 (quirk Q5: in place)
+    matched_gt_inds = mg[sel].to(torch.int64)                                         # :363
+    gt_matched_classes = gt_classes[matched_gt_inds]                                  # :365
+    pred_ious_this_matching = mi[sel]                                                 # :367-369
+    return fg_mask, num_fg, matched_gt_inds, gt_matched_classes, pred_ious_this_matching

@@ -226,3 +226,115 @@ def test_format_outputs_matches_reference_op_chain():
     jl2, _ = format_outputs(plain, ids, hws, (1.0, 1.0), class_ids, None)
     rj2, _ = _ref_format_outputs([None if o is None else o.clone() for o in ref_in], ids, hws, (1.0, 1.0), class_ids)
     assert jl2 == rj2
+
+
+# ---- the stand-alone boundary functions, pinned to goldens produced by the REAL reference (oracle/gen_golden_boundary.py)
+def test_get_in_boxes_info_vs_real_reference():
+    from pl_yolo_b200 import get_in_boxes_info
+    _, g = load("ref_in_boxes_160")
+    gt, xs, ys, es = cu(g["gt"]), cu(g["x_shifts"]), cu(g["y_shifts"]), cu(g["expanded_strides"])
+    fg, both = get_in_boxes_info(gt, es, xs, ys, xs.shape[1], gt.shape[0])     # yolox_loss.py:231 signature
+    assert fg.dtype == torch.bool and both.dtype == torch.bool
+    assert np.array_equal(fg.cpu().numpy(), g["fg_mask"])
+    assert both.shape == tuple(g["both"].shape) and np.array_equal(both.cpu().numpy(), g["both"])
+    # and against the op-for-op replay on CUDA tensors
+    rfg, rboth = R.geometry_prior(gt, es, xs, ys)
+    assert torch.equal(fg, rfg) and torch.equal(both, rboth)
+    # no GT at all: nothing is foreground
+    fg0, both0 = get_in_boxes_info(gt[:0], es, xs, ys, xs.shape[1], 0)
+    assert not fg0.any() and both0.shape == (0, 0)
+
+
+def test_dynamic_k_matching_vs_real_reference():
+    from pl_yolo_b200 import dynamic_k_matching
+    meta, g = load("ref_dynk")
+    for c in meta["cases"]:
+        cost, ious, cls = cu(g[c + "_cost"]), cu(g[c + "_ious"]), cu(g[c + "_cls"])
+        fg = torch.from_numpy(g[c + "_fg_in"].copy()).to(DEV)
+        out = dynamic_k_matching(fg, cost, ious, cls, cost.shape[0])           # yolox_loss.py:318 signature
+        assert out[0] is fg, "fg_mask must be updated in place (yolox_loss.py:361)"
+        assert np.array_equal(fg.cpu().numpy(), g[c + "_fg_out"]), c
+        assert int(out[1]) == int(g[c + "_num_fg"]), c
+        assert np.array_equal(out[2].cpu().numpy(), g[c + "_gt"]), c
+        assert np.array_equal(out[3].cpu().numpy(), g[c + "_mcls"]), c
+        assert np.array_equal(out[4].cpu().numpy(), g[c + "_iou"]), c          # bit-exact
+
+
+def test_dynamic_k_matching_random_vs_replay():
+    """Seeded sweep against the reference op chain on CUDA tensors (stable tie rule == lowest index)."""
+    rng = np.random.default_rng(3)
+    for G, Nc in [(1, 5), (2, 11), (7, 64), (30, 700), (120, 5000)]:
+        ious = cu((rng.uniform(0, 1, (G, Nc)) ** 3).astype(np.float32))
+        cost = cu(np.round(rng.uniform(1, 30, (G, Nc)), 1).astype(np.float32))      # rounded: plenty of exact ties
+        sel, mg, mi, dk, M = ops.dynamic_k_matching_raw(cost, ious)
+        rM, rdk = R.dynamic_k(cost, ious, stable=True)
+        assert torch.equal(dk, rdk.to(torch.int32)), (G, Nc)
+        assert torch.equal(M, rM > 0), (G, Nc)
+        rsel = rM.sum(0) > 0
+        assert torch.equal(sel, rsel)
+        assert torch.equal(mg[sel].long(), rM[:, rsel].argmax(0))
+        assert torch.equal(mi[sel], (rM * ious).sum(0)[rsel])
+
+
+def test_format_outputs_vs_real_reference():
+    """N1 pinned to the real format_outputs (models/evaluators/postprocess.py:95-138, run on CPU tensors by
+    oracle/gen_golden_boundary.py).  On CPU `bboxes /= scale` divides, on CUDA it multiplies by the fp32 reciprocal
+    (what the kernel reproduces): boxes agree to 1 ulp-ish (2e-7 relative), everything else exactly."""
+    from pl_yolo_b200 import format_outputs
+    meta, g = load("ref_format_outputs")
+    B = len(meta["counts"])
+    outs = [None if meta["counts"][i] == 0 else cu(g["in_%d" % i]) for i in range(B)]
+    json_list, det_list = format_outputs(outs, meta["ids"], meta["hws"], tuple(meta["val_size"]), meta["class_ids"], None)
+    assert [j["image_id"] for j in json_list] == g["json_image_id"].tolist()
+    assert [j["category_id"] for j in json_list] == g["json_category_id"].tolist()
+    assert all(j["segmentation"] == [] for j in json_list)
+    # w = x2 - x1 of two coordinates that each differ by at most one ulp of ~1e3 (6e-5): absolute tolerance
+    np.testing.assert_allclose(np.array([j["bbox"] for j in json_list]), g["json_bbox"], rtol=3e-7, atol=2.5e-4)
+    assert np.array_equal(np.array([j["score"] for j in json_list]), g["json_score"])
+    for i in range(B):
+        if outs[i] is not None:   # the reference's in-place rescale is visible to the caller
+            np.testing.assert_allclose(outs[i].cpu().numpy(), g["scaled_%d" % i], rtol=3e-7, atol=1e-5)
+        for c in range(len(meta["class_ids"])):
+            want = g["det_%d_%d" % (i, c)]
+            got = np.asarray(det_list[i][c])
+            assert got.shape == want.shape, (i, c)
+            if want.size:
+                np.testing.assert_allclose(got, want, rtol=3e-7, atol=1e-5)
+
+
+def test_lazy_predictions_torch_function_and_edges():
+    heads = [cu(h) for h in synth.make_heads(2, 160, 80, 5)]
+    ref = R.decode(heads, STRIDES, True)[0]
+    lazy = YOLOXLoss(80, STRIDES, lazy_eval=True).eval()(heads, None)
+    assert torch.equal(torch.max(lazy, dim=2).values, ref.max(dim=2).values)       # __torch_function__ materialises
+    assert torch.equal(torch.cat([lazy, lazy], 0), torch.cat([ref, ref], 0))
+    assert torch.equal(lazy[1, :5], ref[1, :5])
+
+
+def test_fused_training_loss_without_label_rows():
+    """labels [B,0,5]: the reference returns the objectness-only loss (yolox_loss.py:57-62); so does the fused path."""
+    heads = [cu(h).requires_grad_(True) for h in synth.make_heads(2, 160, 80, 6)]
+    empty = torch.zeros((2, 0, 5), device=DEV)
+    fused = YOLOXLoss(80, STRIDES).train()(heads, empty)
+    plain = YOLOXLoss(80, STRIDES, fused_loss=False).train()([h.detach() for h in heads], torch.zeros((2, 1, 5), device=DEV))
+    assert float(fused["loss_iou"]) == 0.0 and float(fused["loss_cls"]) == 0.0
+    assert float(fused["loss"]) == pytest.approx(float(plain["loss"]), rel=1e-5)
+    fused["loss"].backward()
+    assert all(h.grad is not None and torch.isfinite(h.grad).all() for h in heads)
+
+
+def test_format_outputs_short_arguments_and_edited_list():
+    from pl_yolo_b200 import format_outputs
+    p = cu(synth.make_eval_preds(3, 525, 80, 2, size=160.0))
+    outs = postprocess(p, 0.3, 0.5)
+    ref = [None if o is None else o.clone() for o in outs]
+    # fewer image sizes than outputs: zip() semantics, only the first two images are visited
+    j, d = format_outputs(outs, [1, 2], [[100, 200], [300, 150]], (160, 160), list(range(80)))
+    assert {x["image_id"] for x in j} <= {1, 2} and len(d) == 3
+    assert outs[2] is None or torch.equal(outs[2], ref[2])                          # untouched
+    # a caller that filtered an entry since postprocess(): the cached dense result must not be trusted
+    outs2 = postprocess(p, 0.3, 0.5)
+    if outs2[0] is not None and outs2[0].shape[0] > 1:
+        outs2[0] = outs2[0][:1].clone()
+        j2, _ = format_outputs(outs2, [1, 2, 3], [[100, 200, 50], [300, 150, 60]], (160, 160), list(range(80)))
+        assert sum(1 for x in j2 if x["image_id"] == 1) == 1

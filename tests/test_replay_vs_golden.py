@@ -53,3 +53,19 @@ def test_simota_replay(name):
     assert np.array_equal(o["matched_gt"].numpy(), g["matched_gt"])
     assert np.array_equal(o["matched_iou"].numpy(), g["matched_iou"])
     assert np.array_equal(o["num_fg"].numpy(), g["num_fg"])
+
+
+@pytest.mark.parametrize("name", names("sib_"))
+def test_sibling_nms_replay_matches_the_real_decoders(name):
+    """oracle/torch_ops_replay.py yolov3_nms / yolov5_nms vs the real YOLOv3Decoder / YOLOv5Decoder outputs (CPU, bit for bit)."""
+    meta, g = load(name)
+    p = torch.from_numpy(g["predictions"])
+    if meta["kind"] == "sib_v3":
+        outs = R.yolov3_nms(p, meta["conf"], meta["nms"], meta["max_nms"], meta["max_det"])
+    else:
+        outs = R.yolov5_nms(p, meta["conf"], meta["nms"], meta["agnostic"])
+    for i, o in enumerate(outs):
+        c = int(g["counts"][i])
+        assert (0 if o is None else o.shape[0]) == c
+        if c:
+            assert np.array_equal(o.numpy(), g["dets"][i, :c])
