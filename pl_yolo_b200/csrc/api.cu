@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -77,6 +78,14 @@ int make_levels(Levels &lv, const float *const *host_lvl, const int *hs, const i
 }  // namespace plyolo
 
 namespace plyolo {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("PLYOLO_NO_PDL");
+        return !(v && v[0] == '1');
+    }();
+    return on;
+}
+
 bool first_use_on_device(int tag) {
     static std::mutex mu;
     static bool done[8][64] = {};

@@ -60,7 +60,31 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // so no launch ever changes what another host thread relies on (api.cu)
 bool first_use_on_device(int tag);
 
+// PLYOLO_NO_PDL=1 launches every kernel as a plain stream-ordered kernel (A/B measurements, debugging)
+bool pdl_enabled();
+
+// cudaLaunchKernelEx with (optionally) the programmatic-dependent-launch attribute: the kernel may be scheduled while
+// its predecessor in the stream is still running; it orders itself with griddepcontrol.wait (or its own flags)
+template <typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                             Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- device side ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // sigmoid exactly as ATen's CUDA kernel: 1 / (1 + exp(-x)) (bit-equal on B200, tools/probe_aten_cuda.py)
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -592,31 +592,6 @@ static int ensure_kernel_attributes() {
     return PLYOLO_OK;
 }
 
-// PLYOLO_NO_PDL=1 launches the NMS kernels as plain stream-ordered kernels (A/B measurements, debugging)
-static bool pdl_enabled() {
-    static const bool on = [] {
-        const char *v = getenv("PLYOLO_NO_PDL");
-        return !(v && v[0] == '1');
-    }();
-    return on;
-}
-
-template <typename... Args>
-static cudaError_t launch_ex(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
-                             Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
 // `overlap`: the score stage was the persistent kernel (it triggers its dependents at once and publishes the
 // per-image scored-tile counters), so the class-split NMS may start under it.
 static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kPrepThreads) simota_prep_kernel(const SimPara
     extern __shared__ unsigned prep_smem[];  // bitmap [nwords] | word_base [nwords + 1] | this CTA's candidates [A/4 + 128] | in-both count per GT [Lmax]
     __shared__ int s_G, s_warp[kPrepThreads / 32];
     const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();  // the sweep grid may be scheduled behind this one (it waits for our completion itself)
     const int nwords = (p.A + 31) >> 5;
     unsigned *bm_fg = prep_smem;
     int *word_base = reinterpret_cast<int *>(prep_smem + nwords);
@@ -632,6 +633,11 @@ __global__ void __launch_bounds__(kSweepThreads, 4) simota_sweep_kernel(const Si
     __shared__ unsigned short s_hit[kSweepGts][kSweepChunk];
     __shared__ int s_nhit[kSweepGts];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // programmatic dependent launch: everything below reads the prep kernel's results; once they are complete the match
+    // grid may start too — its first phases (in-both lists, row prefetch, exact terms, tight bounds) only need prep's
+    // results, which are then guaranteed visible, and run while this grid drains
+    pdl_wait();
+    pdl_launch_dependents();
     const int gl = warp / kSweepSub, ws = warp % kSweepSub;  // GT of the CTA, part of the GT's hit groups
     const int g = blockIdx.x * kSweepGts + gl;
     const int G = p.meta[b * 8 + 0], Nc = p.meta[b * 8 + 1];
@@ -835,15 +841,10 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     }
 
     SPROF(1);
-    // ---- 1. dynamic k of every GT (:336-340): computed by the IoU sweep
+    // ---- 1. the GT's class / row for the pair loops; its dynamic k (:336-340) comes from the IoU sweep kernel, which may
+    // still be running (programmatic dependent launch): it is read after the bounds below, behind griddepcontrol.wait
     SPROF(2);
     if (half == 0 && lane == 0) {
-        int k = 0;
-        if (live) {
-            k = __ldg(p.dyn_k + (size_t)b * p.Lmax + g);
-            if (!(k < Nc - 1)) sh.nb[gi] = 0;  // quirk Q3: every candidate is taken, no cost needed
-        }
-        sh.k[gi] = k;
         sh.gcls[gi] = gc;
         sh.gidx[gi] = live ? g : 0;
     }
@@ -952,6 +953,15 @@ __global__ void __launch_bounds__(kMatchThreads) simota_match_kernel(const SimPa
     if (kTightAll) {
         __syncthreads();
         tight_pass(npairs, false);
+    }
+    pdl_wait();  // the IoU sweep has completed: dynamic k of every GT
+    if (half == 0 && lane == 0) {
+        int k = 0;
+        if (live) {
+            k = __ldcg(p.dyn_k + (size_t)b * p.Lmax + g);
+            if (!(k < Nc - 1)) sh.nb[gi] = 0;  // quirk Q3: every candidate is taken, no cost needed
+        }
+        sh.k[gi] = k;
     }
     if (tid == 0) { sh.n_eval = 0; sh.n_cand = 0; }
     __syncthreads();
@@ -1326,11 +1336,19 @@ extern "C" int plyolo_simota_f32(const float *preds, const float *labels, int B,
     record_stage_event(0, st);
     simota_prep_kernel<<<dim3(kPrepSplit, B), kPrepThreads, bm, st>>>(p);
     PLYOLO_CHECK_LAUNCH("simota_prep_kernel");
-    simota_sweep_kernel<<<dim3((Lmax + kSweepGts - 1) / kSweepGts, B), kSweepThreads, 0, st>>>(p);
-    PLYOLO_CHECK_LAUNCH("simota_sweep_kernel");
+    const bool pdl = pdl_enabled();
+    if (launch_ex(simota_sweep_kernel, dim3((Lmax + kSweepGts - 1) / kSweepGts, B), dim3(kSweepThreads), 0, st, pdl, p) != cudaSuccess) {
+        set_error("simota_sweep_kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return PLYOLO_ERR_CUDA;
+    }
+    count_launch();
     record_stage_event(1, st);
-    simota_match_kernel<<<dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), kMatchThreads, sizeof(MatchShared), st>>>(p);
-    PLYOLO_CHECK_LAUNCH("simota_match_kernel");
+    if (launch_ex(simota_match_kernel, dim3((Lmax + kGtPerCta - 1) / kGtPerCta, B), dim3(kMatchThreads), sizeof(MatchShared), st, pdl,
+                  p) != cudaSuccess) {
+        set_error("simota_match_kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return PLYOLO_ERR_CUDA;
+    }
+    count_launch();
     record_stage_event(2, st);
     return PLYOLO_OK;
 }
