@@ -231,6 +231,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # the per-step all-gather overlaps the next step's score kernel: leave the communication kernel SMs to run on
+        os.environ.setdefault("PLYOLO_SCORE_SMS_RESERVED", "2")
     from pl_yolo_b200 import YOLOXLoss, _lib, ops, postprocess_dense
     from pl_yolo_b200.distributed import DetectionExchange, fused_det_buffer, shard_range
 
@@ -247,11 +249,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(run_step, steps, finish=None, clocks=True):
-        """W warm-up + `steps` timed steps on `stream`, CUDA events, barrier + synchronize both sides; max over ranks."""
+    def timed(run_step, steps, finish=None, clocks=True, run_many=None):
+        """W warm-up + `steps` timed steps on `stream`, CUDA events, barrier + synchronize both sides; max over ranks.
+        run_many(n) enqueues n consecutive steps (default: run_step(i) for i < n)."""
+        if run_many is None:
+            def run_many(n):
+                for i in range(n):
+                    run_step(i)
         with torch.cuda.stream(stream):
-            for i in range(W):
-                run_step(i)
+            run_many(W)
             if finish is not None:
                 finish()
             barrier()
@@ -261,8 +267,7 @@ def main():
             if sampler:
                 sampler.start()
             e0.record(stream)
-            for i in range(steps):
-                run_step(i)
+            run_many(steps)
             if finish is not None:
                 finish()
             e1.record(stream)
@@ -314,20 +319,61 @@ def main():
         def eager(s):
             ops.decode_postprocess_raw(heads[s], STRIDES, CONF, NMS, False, 10000, 300, 0, out=(bufs[s][1], bufs[s][2], keeps[s]))
 
-        graphs, lpg = capture(eager, n_sets)
-
-        def step(i):
-            s = i % n_sets
+        def step_eager(s):
             if xch:
                 xch.wait_for(s)  # the slot's previous all-gather must have read the buffer before it is rewritten
-            if graphs is not None:
-                graphs[s].replay()
-            else:
-                eager(s)
+            eager(s)
             if xch:
                 xch.submit(s, bufs[s][0], gbufs[s])
 
-        ms, clk, launches = timed(step, steps, finish=xch.finish if xch else None, clocks=clocks)
+        graphs, lpg = capture(eager, n_sets)
+        # One graph per ROUND of n_sets steps: every step's kernels, and (N > 1) every step's all-gather forked onto the
+        # side stream right behind its NMS kernel, so that it runs under the next step's score kernel; the side stream
+        # joins at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
+        # step would cost more than the 48 us of device work) out of the measurement.
+        round_graph = None
+        R_STEPS = n_sets * (4 if xch else 1)  # steps per round: only the round's LAST all-gather is not overlapped
+        if graphs is not None:
+            try:
+                with torch.cuda.stream(stream):
+                    for s in range(n_sets):
+                        step_eager(s)
+                    if xch:
+                        xch.finish()
+                    torch.cuda.synchronize(dev)
+                    if xch:
+                        xch.done = [None] * n_sets
+                    round_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(round_graph, stream=stream):
+                        for s in range(R_STEPS):
+                            step_eager(s % n_sets)
+                        if xch:
+                            xch.finish()
+                    if xch:
+                        xch.done = [None] * n_sets
+                    round_graph.replay()
+                    torch.cuda.synchronize(dev)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("round graph capture failed (%r): stepping graph by graph\n" % (e,))
+                round_graph = None
+                torch.cuda.synchronize(dev)
+                if xch:
+                    xch.done = [None] * n_sets
+
+        def run_many(n):
+            i = 0
+            while i < n:
+                if round_graph is not None and i % n_sets == 0 and i + R_STEPS <= n:
+                    round_graph.replay()
+                    i += R_STEPS
+                    continue
+                if graphs is not None and not xch:
+                    graphs[i % n_sets].replay()
+                else:
+                    step_eager(i % n_sets)
+                i += 1
+
+        ms, clk, launches = timed(None, steps, finish=xch.finish if xch else None, clocks=clocks, run_many=run_many)
         if graphs is not None:
             launches = lpg * steps
         step_s = ms * 1e-3 / steps
@@ -339,7 +385,8 @@ def main():
         L.plyolo_debug_skip_nms(0)
         score_s = ms2 * 1e-3 / min(steps, 40)
         return {"value": world * b_loc * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "batch_per_gpu": b_loc,
-                "anchors": anchors_of(size), "gpu_launches": int(launches), "launch": "cuda_graph" if graphs is not None else "eager",
+                "anchors": anchors_of(size), "gpu_launches": int(launches),
+                "launch": ("cuda_graph (one replay per round of %d steps)" % R_STEPS) if round_graph is not None else ("cuda_graph" if graphs is not None else "eager"),
                 "dets_per_image": float(torch.stack([b[2] for b in bufs]).float().mean()),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "algorithmic_bytes_per_image": bytes_decode_nms(size),
@@ -378,7 +425,7 @@ def main():
     # ------------------------------------------------------------------ cfg2 (headline) and cfg3
     heads_np, labels_np = make_inputs()
     heads, labels = to_dev(heads_np, labels_np)
-    dn = bench_decode_nms(heads, BATCH, SIZE, K, exchange=world > 1, clocks=True)
+    dn = bench_decode_nms(heads, BATCH, SIZE, K, exchange=world > 1 and os.environ.get("BENCH_NO_EXCHANGE") != "1", clocks=True)
     sim = bench_simota(heads, labels, BATCH, SIZE, K, clocks=True)
     sim["workload"] = "YOLOX-s SimOTA assignment batch 32, G~U{1..120} (mean %.1f) [BASELINE configs[2]]" % sim["gt_mean"]
 
@@ -553,7 +600,10 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "anchors": anchors_of(SIZE), "classes": C,
                        "dets_per_image": dn["dets_per_image"], "launch": dn["launch"], "l2": "4 input sets rotated (366 MB > 126 MB L2)",
                        "exchange": "none" if world == 1 else "per step: one NCCL all-gather of the fused padded detections + counts "
-                                                             "(230 KB per rank) on a side stream, overlapped with the next steps"},
+                                                             "(230 KB per rank) on a side stream, overlapped with the next steps; "
+                                                             "score kernel on %d SMs (PLYOLO_SCORE_SMS_RESERVED=%s for the communication "
+                                                             "kernel)" % (148 - int(os.environ.get("PLYOLO_SCORE_SMS_RESERVED", "0")),
+                                                                          os.environ.get("PLYOLO_SCORE_SMS_RESERVED", "0"))},
             "roofline": {"bound": "hbm", "achieved": roof["achieved"], "peak": peak, "unit": "GB/s", "frac": roof["frac"],
                          "traffic": (traffic_bytes("score_kernel") or 0) + (traffic_bytes("nms_fast_kernel") or 0) or None,
                          "peak_source": peak_src,

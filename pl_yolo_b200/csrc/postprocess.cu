@@ -551,12 +551,18 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
 // worst-case tile count for A anchors split into at most PLYOLO_MAX_LEVELS levels
 static int max_tiles(int A) { return (A + kPpTile - 1) / kPpTile + PLYOLO_MAX_LEVELS; }
 
+// SMs the persistent score kernel uses: all of them, minus PLYOLO_SCORE_SMS_RESERVED (default 0).  In multi-GPU
+// evaluation the detection all-gather of step i runs under the score kernel of step i+1 (side stream); the score CTA
+// and the co-resident NMS CTA fill an SM completely, so a communication kernel only finds room on SMs left free.
 static int sm_count() {
     static thread_local int n = 0;
     if (n == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        const char *v = getenv("PLYOLO_SCORE_SMS_RESERVED");
+        const int r = v ? atoi(v) : 0;
+        if (r > 0 && r < n) n -= r;
     }
     return n;
 }
