@@ -231,10 +231,11 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # the per-step all-gather overlaps the next step's score kernel: leave the communication kernel SMs to run on
-        os.environ.setdefault("PLYOLO_SCORE_SMS_RESERVED", "2")
+        if os.environ.get("BENCH_EXCHANGE") == "nccl":  # leave the communication kernel SMs to run on
+            os.environ.setdefault("PLYOLO_SCORE_SMS_RESERVED", "2")
     from pl_yolo_b200 import YOLOXLoss, _lib, ops, postprocess_dense
-    from pl_yolo_b200.distributed import DetectionExchange, fused_det_buffer, shard_range
+    from pl_yolo_b200.distributed import DetectionExchange, PeerDetections, fused_det_buffer, shard_range
+    peer_tables = []
 
     K, W = args.steps, args.warmup
     stream = torch.cuda.Stream(dev)
@@ -311,19 +312,56 @@ def main():
         """Fused decode + postprocess over rotating input sets; with `exchange` the fused detection buffer of every
         step is all-gathered on a side stream.  -> dict"""
         n_sets = len(heads)
-        bufs = [fused_det_buffer(b_loc, 300, dev) for _ in range(n_sets)]
-        keeps = [torch.empty((b_loc, 300), dtype=torch.int32, device=dev) for _ in range(n_sets)]
-        gbufs = [torch.empty((world * bufs[0][0].numel(),), dtype=torch.float32, device=dev) for _ in range(n_sets)] if exchange else None
-        xch = DetectionExchange(dev, n_sets) if exchange else None
+        # N > 1: the detection exchange of every step, into peer-mapped gathered buffers (CUDA IPC over NVLink,
+        # pl_yolo_b200.distributed.PeerDetections), one cross-rank fence per round of steps.  BENCH_EXCHANGE=
+        #   dma (default): every step's finished block is pushed to the other ranks by the copy engines on a side stream,
+        #                  under the next step's score kernel — no SM, no collective kernel;
+        #   stores:        the NMS kernels store every row to the peers themselves (plyolo_decode_postprocess_bcast_f32);
+        #   nccl:          one NCCL all-gather of the fused buffer per step on a side stream.
+        pdx = None
+        xmode = os.environ.get("BENCH_EXCHANGE", "dma")  # dma | stores | nccl
+        if exchange and xmode in ("dma", "stores"):
+            try:
+                pdx = PeerDetections(b_loc, 300, dev, slots=n_sets)
+                peer_tables.append(pdx)
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("peer-store exchange unavailable (%r): NCCL all-gather per step\n" % (e,))
+                pdx = None
+        if pdx is not None:
+            outs = [pdx.outputs(s) for s in range(n_sets)]
+            bufs = [(None, o[0], o[1]) for o in outs]
+            keeps = [o[2] for o in outs]
+            peers = [pdx.peers(s) if xmode == "stores" else None for s in range(n_sets)]
+            gbufs = None
+            xch = DetectionExchange(dev, n_sets) if xmode == "dma" else None
+            fence_t = torch.zeros(1, device=dev)
+        else:
+            bufs = [fused_det_buffer(b_loc, 300, dev) for _ in range(n_sets)]
+            keeps = [torch.empty((b_loc, 300), dtype=torch.int32, device=dev) for _ in range(n_sets)]
+            peers = [None] * n_sets
+            gbufs = [torch.empty((world * bufs[0][0].numel(),), dtype=torch.float32, device=dev) for _ in range(n_sets)] if exchange else None
+            xch = DetectionExchange(dev, n_sets) if exchange else None
+        fake = None
+        if os.environ.get("BENCH_FAKE_EXCHANGE") == "1" and xch is None and pdx is None:   # diagnosis: what the fork / join alone costs
+            xch, fake = DetectionExchange(dev, n_sets), torch.zeros(64, device=dev)
+
+        def fence():
+            if pdx is not None:
+                dist.all_reduce(fence_t)  # every rank's stores of the round have landed before anybody goes on
 
         def eager(s):
-            ops.decode_postprocess_raw(heads[s], STRIDES, CONF, NMS, False, 10000, 300, 0, out=(bufs[s][1], bufs[s][2], keeps[s]))
+            ops.decode_postprocess_raw(heads[s], STRIDES, CONF, NMS, False, 10000, 300, 0, out=(bufs[s][1], bufs[s][2], keeps[s]),
+                                       peers=peers[s])
 
         def step_eager(s):
             if xch:
                 xch.wait_for(s)  # the slot's previous all-gather must have read the buffer before it is rewritten
             eager(s)
-            if xch:
+            if fake is not None:
+                xch.submit(s, push=lambda: fake.zero_())
+            elif xch and pdx is not None:
+                xch.submit(s, push=lambda: pdx.push(s))
+            elif xch:
                 xch.submit(s, bufs[s][0], gbufs[s])
 
         graphs, lpg = capture(eager, n_sets)
@@ -332,7 +370,7 @@ def main():
         # joins at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
         # step would cost more than the 48 us of device work) out of the measurement.
         round_graph = None
-        R_STEPS = n_sets * (4 if xch else 1)  # steps per round: only the round's LAST all-gather is not overlapped
+        R_STEPS = n_sets * (4 if (xch or pdx) else 1)  # steps per round (one fence / one exposed all-gather per round)
         if graphs is not None:
             try:
                 with torch.cuda.stream(stream):
@@ -340,6 +378,7 @@ def main():
                         step_eager(s)
                     if xch:
                         xch.finish()
+                    fence()
                     torch.cuda.synchronize(dev)
                     if xch:
                         xch.done = [None] * n_sets
@@ -349,6 +388,7 @@ def main():
                             step_eager(s % n_sets)
                         if xch:
                             xch.finish()
+                        fence()
                     if xch:
                         xch.done = [None] * n_sets
                     round_graph.replay()
@@ -373,7 +413,21 @@ def main():
                     step_eager(i % n_sets)
                 i += 1
 
-        ms, clk, launches = timed(None, steps, finish=xch.finish if xch else None, clocks=clocks, run_many=run_many)
+        def finish():
+            if xch:
+                xch.finish()
+            if pdx is not None and finish.pending:
+                fence()
+            finish.pending = False
+
+        finish.pending = False
+        _run_many = run_many
+
+        def run_many(n):  # noqa: F811
+            finish.pending = (n % R_STEPS != 0) or round_graph is None  # eager steps since the last fence
+            _run_many(n)
+
+        ms, clk, launches = timed(None, steps, finish=finish if (xch or pdx) else None, clocks=clocks, run_many=run_many)
         if graphs is not None:
             launches = lpg * steps
         step_s = ms * 1e-3 / steps
@@ -393,7 +447,11 @@ def main():
                              "score_stage": {"us": score_s * 1e6, "achieved": b_loc * bytes_decode_nms(size) / score_s / 1e9,
                                              "frac": b_loc * bytes_decode_nms(size) / score_s / 1e9 / peak,
                                              "what": "memset + score_kernel<fused> alone (reads every head-map byte once)"}},
-                "clocks": clk, "_bufs": bufs, "_gbufs": gbufs}
+                "exchange": (("copy-engine pushes of the finished block into the peers' gathered buffers (CUDA IPC over NVLink) on a side "
+                              "stream, one fence per %d steps" if xmode == "dma" else
+                              "peer stores from the NMS kernels (CUDA IPC over NVLink), one fence per %d steps") % R_STEPS) if pdx is not None else
+                            ("NCCL all-gather per step on a side stream" if xch else "none"),
+                "clocks": clk}
 
     def bench_simota(heads, labels, b_loc, size, steps, clocks=False):
         n_sets = len(heads)
@@ -599,11 +657,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "anchors": anchors_of(SIZE), "classes": C,
                        "dets_per_image": dn["dets_per_image"], "launch": dn["launch"], "l2": "4 input sets rotated (366 MB > 126 MB L2)",
-                       "exchange": "none" if world == 1 else "per step: one NCCL all-gather of the fused padded detections + counts "
-                                                             "(230 KB per rank) on a side stream, overlapped with the next steps; "
-                                                             "score kernel on %d SMs (PLYOLO_SCORE_SMS_RESERVED=%s for the communication "
-                                                             "kernel)" % (148 - int(os.environ.get("PLYOLO_SCORE_SMS_RESERVED", "0")),
-                                                                          os.environ.get("PLYOLO_SCORE_SMS_RESERVED", "0"))},
+                       "exchange": "per step: " + dn["exchange"]},
             "roofline": {"bound": "hbm", "achieved": roof["achieved"], "peak": peak, "unit": "GB/s", "frac": roof["frac"],
                          "traffic": (traffic_bytes("score_kernel") or 0) + (traffic_bytes("nms_fast_kernel") or 0) or None,
                          "peak_source": peak_src,
@@ -628,6 +682,8 @@ def main():
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        for t in peer_tables:
+            t.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -40,6 +40,7 @@ extern "C" {
 #define PLYOLO_ERR_NO_DEVICE (-4)   /* no sm_100 device: there is no CPU fallback */
 
 #define PLYOLO_MAX_LEVELS 8
+#define PLYOLO_MAX_PEERS 15         /* other ranks a call can store its detections to (16 GPUs per NVLink domain) */
 #define PLYOLO_MAX_CLASSES 91       /* ATen's CUDA reduce tree is reproduced bit-exactly up to 91 inputs */
 
 /* NMS arithmetic flavor: OR of independent bits. 0 reproduces the reference on CUDA tensors
@@ -60,6 +61,16 @@ typedef void *plyolo_stream_t; /* cudaStream_t */
 
 int plyolo_version(void);
 const char *plyolo_last_error(void);
+/* Peer-visible buffers for plyolo_decode_postprocess_bcast_f32 (CUDA IPC, one process per GPU):
+ *   plyolo_peer_alloc  cudaMalloc + zero + export: *ptr on the current device, handle64 = 64 opaque bytes to send to the
+ *                      other ranks;  plyolo_peer_open maps another rank's buffer for kernels of the CURRENT device;
+ *   plyolo_peer_close  releases a mapping (opened != 0) or frees an allocation (opened == 0). */
+int plyolo_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int plyolo_peer_open(const unsigned char *handle64, void **ptr);
+int plyolo_peer_close(void *ptr, int opened);
+/* lets kernels running on the current device store to memory of `peer_device` (cudaDeviceEnablePeerAccess; needed once
+ * per process and peer before plyolo_decode_postprocess_bcast_f32 is given buffers of that device) */
+int plyolo_enable_peer_access(int peer_device);
 /* number of kernels the calling thread has launched through this library so far (bench accounting) */
 unsigned long long plyolo_launch_count(void);
 
@@ -121,6 +132,19 @@ int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, c
                                   double nms_thre, int class_agnostic, int max_nms, int max_det,
                                   int flavor, float *dets, int32_t *counts, int32_t *keep_idx,
                                   void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+
+/* Multi-GPU evaluation: the same call, but the NMS kernels ALSO store every image's rows and count straight into the
+ * other ranks' gathered buffers (peer memory mapped over NVLink / NVSwitch, e.g. CUDA IPC) — the detection all-gather of
+ * SURVEY 8e happens inside the kernels, no collective is launched.
+ *   host_peer_dets / host_peer_counts   host arrays of n_peers device pointers, each pointing at THIS rank's block
+ *                                       ([B, max_det, 6] / [B]) inside a peer's gathered buffer; n_peers <= PLYOLO_MAX_PEERS
+ * The caller orders consumption across ranks (a barrier after the step's stream work). */
+int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl, const int *hs, const int *ws, const int *strides,
+                                        int n_levels, int B, int C, double conf_thre, double nms_thre, int class_agnostic,
+                                        int max_nms, int max_det, int flavor, float *dets, int32_t *counts,
+                                        int32_t *keep_idx, int n_peers, float *const *host_peer_dets,
+                                        int32_t *const *host_peer_counts, void *workspace, size_t workspace_bytes,
+                                        plyolo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SimOTA assignment — replaces the per-image block of YOLOXLoss.__call__ (yolox_loss.py:43-118):

@@ -28,6 +28,14 @@ def _declare(lib):
     lib.plyolo_version.restype = c_int
     lib.plyolo_last_error.restype = c_char_p
     lib.plyolo_launch_count.restype = c_ulonglong
+    lib.plyolo_peer_alloc.restype = c_int
+    lib.plyolo_peer_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_char_p]
+    lib.plyolo_peer_open.restype = c_int
+    lib.plyolo_peer_open.argtypes = [c_char_p, POINTER(c_void_p)]
+    lib.plyolo_peer_close.restype = c_int
+    lib.plyolo_peer_close.argtypes = [c_void_p, c_int]
+    lib.plyolo_enable_peer_access.restype = c_int
+    lib.plyolo_enable_peer_access.argtypes = [c_int]
     lib.plyolo_decode_f32.restype = c_int
     lib.plyolo_decode_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, vp, vp, c_int, vp]
     lib.plyolo_postprocess_workspace_bytes.restype = c_size_t
@@ -41,6 +49,10 @@ def _declare(lib):
     lib.plyolo_decode_postprocess_f32.restype = c_int
     lib.plyolo_decode_postprocess_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, c_double,
                                                   c_double, c_int, c_int, c_int, c_int, vp, vp, vp, vp, c_size_t, vp]
+    lib.plyolo_decode_postprocess_bcast_f32.restype = c_int
+    lib.plyolo_decode_postprocess_bcast_f32.argtypes = [POINTER(c_void_p), ip, ip, ip, c_int, c_int, c_int, c_double,
+                                                        c_double, c_int, c_int, c_int, c_int, vp, vp, vp, c_int,
+                                                        POINTER(c_void_p), POINTER(c_void_p), vp, c_size_t, vp]
     lib.plyolo_simota_workspace_bytes.restype = c_size_t
     lib.plyolo_simota_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.plyolo_simota_f32.restype = c_int

@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -101,6 +102,62 @@ bool first_use_on_device(int tag) {
 extern "C" {
 
 int plyolo_version(void) { return PLYOLO_VERSION; }
+
+int plyolo_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64) {
+    if (!ptr || !handle64 || bytes == 0) { plyolo::set_error("plyolo_peer_alloc: bad argument"); return PLYOLO_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        plyolo::set_error("plyolo_peer_alloc: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PLYOLO_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return PLYOLO_OK;
+}
+
+int plyolo_peer_open(const unsigned char *handle64, void **ptr) {
+    if (!ptr || !handle64) { plyolo::set_error("plyolo_peer_open: bad argument"); return PLYOLO_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    // opened from the CURRENT device: kernels of this device may then store to the other device's buffer over NVLink
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        plyolo::set_error("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PLYOLO_ERR_CUDA;
+    }
+    return PLYOLO_OK;
+}
+
+int plyolo_peer_close(void *ptr, int opened) {
+    const cudaError_t e = opened ? cudaIpcCloseMemHandle(ptr) : cudaFree(ptr);
+    cudaGetLastError();
+    return e == cudaSuccess ? PLYOLO_OK : PLYOLO_ERR_CUDA;
+}
+
+int plyolo_enable_peer_access(int peer_device) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PLYOLO_ERR_NO_DEVICE;
+    if (peer_device == dev) return PLYOLO_OK;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev, peer_device) != cudaSuccess || !can) {
+        cudaGetLastError();
+        plyolo::set_error("device %d cannot access device %d as a peer", dev, peer_device);
+        return PLYOLO_ERR_INVALID;
+    }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        plyolo::set_error("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+        cudaGetLastError();
+        return PLYOLO_ERR_CUDA;
+    }
+    cudaGetLastError();
+    return PLYOLO_OK;
+}
 const char *plyolo_last_error(void) { return plyolo::g_err; }
 unsigned long long plyolo_launch_count(void) { return plyolo::g_launches; }
 // debug hook (not part of include/plyolo.h): three cudaEvent_t handles (or nulls to disarm) that the two-kernel

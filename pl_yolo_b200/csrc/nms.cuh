@@ -115,8 +115,29 @@ struct NmsParams {
     float *dets;
     int32_t *counts;
     int32_t *keep_idx;
+    // multi-GPU evaluation: the image's rows and count are ALSO stored straight into the other ranks' gathered
+    // buffers (peer memory over NVLink / NVSwitch) — the detection all-gather happens inside the NMS kernels
+    int n_peers;
+    float *peer_dets[PLYOLO_MAX_PEERS];      // each already offset to this rank's block [B, max_det, 6]
+    int32_t *peer_counts[PLYOLO_MAX_PEERS];  // each already offset to this rank's block [B]
     long long *prof;  // debug: [B][16] phase timestamps (clock64) or null
 };
+
+// one output row / the image's count, to the caller's buffers and to every peer's
+__device__ __forceinline__ void store_row6(const NmsParams &p, const int b, const int row, const float2 r0, const float2 r1,
+                                           const float2 r2) {
+    const size_t o = ((size_t)b * p.max_det + row) * 6;
+    float2 *d = reinterpret_cast<float2 *>(p.dets + o);
+    d[0] = r0; d[1] = r1; d[2] = r2;
+    for (int r = 0; r < p.n_peers; ++r) {
+        float2 *q = reinterpret_cast<float2 *>(p.peer_dets[r] + o);
+        q[0] = r0; q[1] = r1; q[2] = r2;
+    }
+}
+__device__ __forceinline__ void store_count(const NmsParams &p, const int b, const int n) {
+    p.counts[b] = n;
+    for (int r = 0; r < p.n_peers; ++r) p.peer_counts[r][b] = n;
+}
 
 #define NMS_PROF(slot)                                                                   \
     do {                                                                                 \
@@ -403,21 +424,18 @@ __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, cons
         return;
     }
     for (int i = threadIdx.x; i < p.max_det; i += kNmsThreads) {
-        float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
         if (i < nkept) {
             const int slot = slot_of(i);
             const float4 bx = p.ws.box[slot0 + slot];
             const int meta = p.ws.meta[slot0 + slot];
-            d[0] = make_float2(bx.x, bx.y);
-            d[1] = make_float2(bx.z, bx.w);
-            d[2] = make_float2(p.ws.score[slot0 + slot], (float)(meta >> 24));
+            store_row6(p, b, i, make_float2(bx.x, bx.y), make_float2(bx.z, bx.w), make_float2(p.ws.score[slot0 + slot], (float)(meta >> 24)));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = meta & 0xffffff;
         } else {
-            d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
+            store_row6(p, b, i, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
         }
     }
-    if (threadIdx.x == 0) p.counts[b] = nkept;
+    if (threadIdx.x == 0) store_count(p, b, nkept);
 }
 
 // The whole NMS of image b by the calling CTA (kNmsThreads threads, all of them must call).

@@ -166,11 +166,10 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     if (total == 0) {  // no candidate: postprocess.py:26-27 leaves None (count 0, zero rows)
         if (g == 0) {
             for (int i = tid; i < p.max_det; i += kFastThreads) {
-                float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
-                d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
+                store_row6(p, b, i, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f));
                 if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
             }
-            if (tid == 0) p.counts[b] = 0;
+            if (tid == 0) store_count(p, b, 0);
         }
         FAST_EXIT();
     }
@@ -478,20 +477,16 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
             const int bi = kidx2[i];
             const float4 bx = sbox[bi];
             const float sc = ordered_float(~(unsigned)(key >> kFastAnchorBits));  // the key holds the score bits
-            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + rank) * 6);
-            d[0] = make_float2(bx.x, bx.y);
-            d[1] = make_float2(bx.z, bx.w);
-            d[2] = make_float2(sc, (float)scls[bi]);
+            store_row6(p, b, rank, make_float2(bx.x, bx.y), make_float2(bx.z, bx.w), make_float2(sc, (float)scls[bi]));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = (int)(key & ((1ull << kFastAnchorBits) - 1ull));
         }
     }
     if (g == 0) {
         for (int i = nkept + tid; i < p.max_det; i += kFastThreads) {
-            float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + i) * 6);
-            d[0] = make_float2(0.f, 0.f); d[1] = make_float2(0.f, 0.f); d[2] = make_float2(0.f, 0.f);
+            store_row6(p, b, i, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
         }
-        if (tid == 0) p.counts[b] = nkept;
+        if (tid == 0) store_count(p, b, nkept);
     }
     FPROF(8);
     FAST_EXIT();

@@ -602,8 +602,14 @@ static int ensure_kernel_attributes() {
 // per-image scored-tile counters), so the class-split NMS may start under it.
 static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
                    const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream,
-                   int variant = PLYOLO_NMS_YOLOX) {
+                   int variant = PLYOLO_NMS_YOLOX, int n_peers = 0, float *const *peer_dets = nullptr,
+                   int32_t *const *peer_counts = nullptr) {
     NmsParams np;
+    np.n_peers = n_peers;
+    for (int r = 0; r < PLYOLO_MAX_PEERS; ++r) {
+        np.peer_dets[r] = r < n_peers ? peer_dets[r] : nullptr;
+        np.peer_counts[r] = r < n_peers ? peer_counts[r] : nullptr;
+    }
     np.B = B; np.NT = NT; np.max_nms = max_nms; np.max_det = max_det; np.flavor = flavor;
     np.variant = variant;
     np.fixed_span = variant == PLYOLO_NMS_YOLOV5 ? 4096.f : 0.f;             // yolov5_decoder.py:27, :70
@@ -768,12 +774,16 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
                    overlap, (cudaStream_t)stream);
 }
 
-extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
-                                             const int *strides, int n_levels, int B, int C, double conf_thre,
-                                             double nms_thre, int class_agnostic, int max_nms, int max_det,
-                                             int flavor, float *dets, int32_t *counts, int32_t *keep_idx,
-                                             void *workspace, size_t workspace_bytes, plyolo_stream_t stream) {
+extern "C" int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl, const int *hs, const int *ws,
+                                                   const int *strides, int n_levels, int B, int C, double conf_thre,
+                                                   double nms_thre, int class_agnostic, int max_nms, int max_det,
+                                                   int flavor, float *dets, int32_t *counts, int32_t *keep_idx, int n_peers,
+                                                   float *const *host_peer_dets, int32_t *const *host_peer_counts,
+                                                   void *workspace, size_t workspace_bytes, plyolo_stream_t stream) {
     using namespace plyolo;
+    PLYOLO_REQUIRE(n_peers >= 0 && n_peers <= PLYOLO_MAX_PEERS, "n_peers=%d not in [0,%d]", n_peers, PLYOLO_MAX_PEERS);
+    for (int r = 0; r < n_peers; ++r)
+        PLYOLO_REQUIRE(host_peer_dets && host_peer_counts && host_peer_dets[r] && host_peer_counts[r], "peer %d: null pointer", r);
     ScoreParams sp;
     int rc = make_levels(sp.lv, host_lvl, hs, ws, strides, n_levels, kPpTile);
     if (rc != PLYOLO_OK) return rc;
@@ -795,7 +805,17 @@ extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const
     rc = launch_score<true>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   overlap, (cudaStream_t)stream);
+                   overlap, (cudaStream_t)stream, PLYOLO_NMS_YOLOX, n_peers, host_peer_dets, host_peer_counts);
+}
+
+extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
+                                             const int *strides, int n_levels, int B, int C, double conf_thre,
+                                             double nms_thre, int class_agnostic, int max_nms, int max_det,
+                                             int flavor, float *dets, int32_t *counts, int32_t *keep_idx,
+                                             void *workspace, size_t workspace_bytes, plyolo_stream_t stream) {
+    return plyolo_decode_postprocess_bcast_f32(host_lvl, hs, ws, strides, n_levels, B, C, conf_thre, nms_thre, class_agnostic,
+                                               max_nms, max_det, flavor, dets, counts, keep_idx, 0, nullptr, nullptr, workspace,
+                                               workspace_bytes, stream);
 }
 
 extern "C" int plyolo_postprocess_yolo_f32(const float *preds, int B, int N, int C, double conf_thre, double nms_thre,

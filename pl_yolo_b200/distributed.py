@@ -13,6 +13,8 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
 
 def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous image range [lo, hi) of `rank`; earlier ranks take the remainder."""
@@ -98,15 +100,113 @@ class DetectionExchange:
         if self.done[slot] is not None:
             torch.cuda.current_stream().wait_event(self.done[slot])
 
-    def submit(self, slot: int, buf: torch.Tensor, gbuf: torch.Tensor) -> None:
+    def submit(self, slot: int, buf: torch.Tensor = None, gbuf: torch.Tensor = None, push=None) -> None:
+        """Default: NCCL all-gather of `buf` into `gbuf`; `push`: any callable that enqueues the exchange on the
+        current (side) stream instead, e.g. PeerDetections.push (copy-engine peer copies, no SM at all)."""
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream())
         self.side.wait_event(ready)
         with torch.cuda.stream(self.side):
-            dist.all_gather_into_tensor(gbuf, buf, group=self.group)
+            if push is not None:
+                push()
+            else:
+                dist.all_gather_into_tensor(gbuf, buf, group=self.group)
             ev = torch.cuda.Event()
             ev.record(self.side)
         self.done[slot] = ev
 
     def finish(self) -> None:
         torch.cuda.current_stream().wait_stream(self.side)
+
+
+class _DevMem:
+    """A raw device allocation seen through __cuda_array_interface__ (zero-copy view for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, n_float: int):
+        self.__cuda_array_interface__ = {"shape": (n_float,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _as_tensor(ptr: int, n_float: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DevMem(ptr, n_float), device=device)
+
+
+class PeerDetections:
+    """Gathered detection buffers that the NMS kernels fill directly on every rank (no collective).
+
+    Every rank owns `slots` gathered buffers laid out like `fused_det_buffer` per rank block,
+    `[world][b_loc * max_det * 6 floats | b_loc int32]`, and maps the other ranks' buffers into its address space through
+    CUDA IPC (plyolo_peer_alloc / plyolo_peer_open; the handles travel once with all_gather_object).  `outputs(slot)` gives the local views the C ABI writes
+    (`dets`, `counts`: this rank's own block of its own buffer) and `peers(slot)` the addresses of this rank's block
+    inside every OTHER rank's buffer: pass both to `ops.decode_postprocess_raw(..., out=..., peers=...)` and the
+    all-gather of SURVEY §8e happens inside `nms_fast_kernel` / `nms_general_kernel` as plain stores over NVLink.
+    `fence()` orders consumption across ranks (barrier after the stream's work)."""
+
+    def __init__(self, b_loc: int, max_det: int, device, slots: int = 1, group=None):
+        import ctypes
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b_loc, self.max_det, self.group = b_loc, max_det, group
+        self.block = b_loc * max_det * 6 + b_loc          # floats per rank block
+        n_float = self.world * self.block
+        L = _lib.lib()
+        self._owned, self._opened = [], []
+        self.local, handles = [], []
+        with torch.cuda.device(device):
+            for _ in range(slots):
+                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                _lib.check(L.plyolo_peer_alloc(n_float * 4, ctypes.byref(ptr), h), "plyolo_peer_alloc")
+                self._owned.append(ptr.value)
+                handles.append(h.raw)
+                self.local.append(_as_tensor(ptr.value, n_float, device))
+            every = [None] * self.world
+            dist.all_gather_object(every, handles, group=group)
+            self.remote_ptr = []   # [slot][rank] -> device address of that rank's gathered buffer (None for this rank)
+            for s in range(slots):
+                row = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        row.append(None)
+                        continue
+                    ptr = ctypes.c_void_p()
+                    _lib.check(L.plyolo_peer_open(every[r][s], ctypes.byref(ptr)), "plyolo_peer_open")
+                    self._opened.append(ptr.value)
+                    row.append(ptr.value)
+                self.remote_ptr.append(row)
+            self._remote_views = [[_as_tensor(p, n_float, device) for p in row if p is not None] for row in self.remote_ptr]
+        self.keep = [torch.empty((b_loc, max_det), dtype=torch.int32, device=device) for _ in range(slots)]
+
+    def close(self) -> None:
+        L = _lib.lib()
+        torch.cuda.synchronize()
+        for p in self._opened:
+            L.plyolo_peer_close(p, 1)
+        dist.barrier(group=self.group)   # nobody maps our buffers any more
+        for p in self._owned:
+            L.plyolo_peer_close(p, 0)
+        self._opened, self._owned, self.local, self._remote_views = [], [], [], []
+
+    def outputs(self, slot: int):
+        base = self.local[slot][self.rank * self.block:(self.rank + 1) * self.block]
+        n = self.b_loc * self.max_det * 6
+        return base[:n].view(self.b_loc, self.max_det, 6), base[n:].view(torch.int32), self.keep[slot]
+
+    def peers(self, slot: int):
+        n = self.b_loc * self.max_det * 6
+        off = self.rank * self.block * 4
+        pd = [p + off for p in self.remote_ptr[slot] if p is not None]
+        return pd, [p + n * 4 for p in pd]
+
+    def push(self, slot: int) -> None:
+        """Copies this rank's finished block into every other rank's gathered buffer with plain device-to-device copies
+        on the current stream: peer-mapped addresses, so the copy engines move the 230 KB over NVLink and no SM is
+        involved (use it on a side stream: DetectionExchange.submit(slot, push=...))."""
+        lo, hi = self.rank * self.block, (self.rank + 1) * self.block
+        src = self.local[slot][lo:hi]
+        for t in self._remote_views[slot]:
+            t[lo:hi].copy_(src, non_blocking=True)
+
+    def gathered(self, slot: int):
+        return split_gathered(self.local[slot], self.world, self.b_loc, self.max_det)
+
+    def fence(self) -> None:
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)

@@ -156,8 +156,10 @@ def postprocess_yolo_raw(preds: torch.Tensor, conf_thre: float, nms_thre: float,
 
 def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_thre: float, nms_thre: float,
                            class_agnostic: bool, max_nms: int, max_det: int, flavor: int,
-                           out=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Fused decode + postprocess from the head maps (reads them once; preds never materialised)."""
+                           out=None, peers=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fused decode + postprocess from the head maps (reads them once; preds never materialised).
+    peers = (dets_ptrs, counts_ptrs): device addresses of this rank's block inside the OTHER ranks' gathered buffers
+    (peer memory): the NMS kernels store every row there too (pl_yolo_b200.distributed.PeerDetections)."""
     xs, B, C, hs, ws_, A = _levels(inputs, strides)
     dev = xs[0].device
     dets, counts, keep = _det_outputs(B, max_det, dev, out)
@@ -165,12 +167,14 @@ def decode_postprocess_raw(inputs: List[torch.Tensor], strides: List[int], conf_
     with torch.cuda.device(dev):
         nbytes = L.plyolo_postprocess_workspace_bytes(B, A)
         ws = _workspace("post", nbytes, dev)
-        rc = L.plyolo_decode_postprocess_f32(_lib.ptr_array([x.data_ptr() for x in xs]), _lib.int_array(hs),
-                                             _lib.int_array(ws_), _lib.int_array(strides), len(xs), B, C,
-                                             float(conf_thre), float(nms_thre), int(class_agnostic), int(max_nms),
-                                             int(max_det), int(flavor), dets.data_ptr(), counts.data_ptr(),
-                                             keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
-    _lib.check(rc, "plyolo_decode_postprocess_f32")
+        pd, pc = peers if peers is not None else ((), ())
+        rc = L.plyolo_decode_postprocess_bcast_f32(_lib.ptr_array([x.data_ptr() for x in xs]), _lib.int_array(hs),
+                                                   _lib.int_array(ws_), _lib.int_array(strides), len(xs), B, C,
+                                                   float(conf_thre), float(nms_thre), int(class_agnostic), int(max_nms),
+                                                   int(max_det), int(flavor), dets.data_ptr(), counts.data_ptr(),
+                                                   keep.data_ptr(), len(pd), _lib.ptr_array(list(pd) or [0]),
+                                                   _lib.ptr_array(list(pc) or [0]), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_decode_postprocess_bcast_f32")
     return dets, counts, keep
 
 
