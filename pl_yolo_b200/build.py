@@ -16,6 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libplyolo.so")
 SOURCES = ["api.cu", "decode.cu", "postprocess.cu", "simota.cu", "simota_ops.cu", "loss.cu", "evaluator.cu"]
+# postprocess.cu launches nms_general_kernel from the device (CUDA dynamic parallelism): relocatable device code
+RDC = {"postprocess.cu": ["-rdc=true"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC", "--cudart", "static",
@@ -48,7 +50,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *RDC.get(src, []), *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -59,7 +61,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
             sys.stderr.write(log)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-o", out, *objs]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-o", out, *objs, "-lcudadevrt"]
     subprocess.run(link, check=True)
     return out
 

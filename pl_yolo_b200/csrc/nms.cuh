@@ -107,6 +107,8 @@ struct NmsParams {
     int B, NT, max_nms, max_det, flavor, agnostic, sort_cap, fast_cap;
     int variant;      // PLYOLO_NMS_*: 0 = postprocess.py / batched_nms; YOLOv3 / YOLOv5 decoder call sites otherwise (general path only)
     float fixed_span; // > 0: class offset = class * fixed_span (yolov5_decoder.py:70) instead of max_coordinate + 1
+    int only_image;   // nms_general_kernel launched from the device for ONE image (>= 0), else -1: one CTA per image
+    unsigned general_smem;  // dynamic shared memory of nms_general_kernel (for the device-side launch)
     int all_general;  // nms_general_kernel: every image takes the general path (no class-split kernel ran)
     int wait_tiles;   // nms_fast_kernel: spin on the image's scored-tile counter (the score kernel may still be running)
     float thr_f;
@@ -298,7 +300,7 @@ __device__ __forceinline__ void warp_sort_regs(unsigned long long *k, const int 
 constexpr int kSortE = 8;  // keys per lane of the largest register block (256 keys)
 
 // Ascending sort of k[0, n) (shared memory) by one warp, any n.
-__device__ __noinline__ void warp_sort(unsigned long long *k, const int n) {
+__device__ __forceinline__ void warp_sort(unsigned long long *k, const int n) {
     const int lane = threadIdx.x & 31;
     if (n <= 1) return;
     if (n <= 32) return warp_sort_regs<1>(k, n);
@@ -441,7 +443,7 @@ __device__ __forceinline__ void write_dets(const NmsParams &p, const int b, cons
 // The whole NMS of image b by the calling CTA (kNmsThreads threads, all of them must call).
 // smem_raw: nms_smem_bytes(...) bytes of 16-byte aligned dynamic shared memory:
 // (layout: see nms_core_bytes)
-__device__ __noinline__ void nms_image(const NmsParams &p, const int b, unsigned char *smem_raw) {
+__device__ __forceinline__ void nms_image(const NmsParams &p, const int b, unsigned char *smem_raw) {
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);  // [sort_cap] / fast: [fast_cap]
     unsigned char *region = smem_raw + (size_t)p.sort_cap * 8;                    // general path buffers
     float4 *kept_fast = reinterpret_cast<float4 *>(smem_raw + (size_t)p.fast_cap * 8);   // [fast_cap]
@@ -866,7 +868,7 @@ __device__ __forceinline__ void team_sort_e(unsigned long long *k, const int n, 
     }
 }
 
-__device__ __noinline__ void team_sort(unsigned long long *k, const int n, const int tw, const int bar_id) {
+__device__ __forceinline__ void team_sort(unsigned long long *k, const int n, const int tw, const int bar_id) {
     if (n <= 512) team_sort_e<2>(k, n, tw, bar_id);
     else if (n <= 1024) team_sort_e<4>(k, n, tw, bar_id);
     else team_sort_e<8>(k, n, tw, bar_id);
@@ -875,17 +877,20 @@ __device__ __noinline__ void team_sort(unsigned long long *k, const int n, const
 constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a team of 8 warps
 
 // ---- general path: one CTA per image that needs it ------------------------------------------------------
-// Launched after nms_fast_kernel (nms_fast.cuh).  An image is redone here, exactly, when the class-split kernel
-// raised its flag (max_nms truncation, a class group above its capacity, too many cross boxes, a cross-class pair
-// that suppresses, list overflows) or when the call as a whole cannot use the class split (`all_general`:
-// class-agnostic NMS, very large max_det, anchors beyond the fast key layout).
+// An image is redone here, exactly, when the class-split kernel (nms_fast.cuh) finds that it cannot handle it
+// (max_nms truncation, a class group above its capacity, a cross-class pair that suppresses, list overflows): that
+// kernel then launches this one FROM THE DEVICE for the one image (CUDA dynamic parallelism, fire-and-forget: the images
+// that need it run side by side, and the stream does not move on before they have finished) — an idle launch of 1024-thread /
+// 180 KB CTAs from the host costs 8.6 us per step (measured), so the host only launches it when the call as a whole
+// cannot use the class split (`all_general`: class-agnostic NMS, the YOLOv3 / YOLOv5 call sites, very large max_det,
+// anchors beyond the fast key layout).
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_general_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     // programmatic dependent launch: the CTAs may be scheduled while the previous kernel drains; everything below
     // needs its results
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int b = blockIdx.x;
-    if (!p.all_general && __ldcg(&p.ws.ctr[b * kImgCtr + kCtrGeneral]) == 0) return;
+    const int b = p.only_image >= 0 ? p.only_image : (int)blockIdx.x;
+    if (p.only_image < 0 && !p.all_general && __ldcg(&p.ws.ctr[b * kImgCtr + kCtrGeneral]) == 0) return;
     nms_image(p, b, nms_smem);
 }
 

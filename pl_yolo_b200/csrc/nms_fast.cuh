@@ -65,6 +65,16 @@ __device__ __forceinline__ float4 shift_box(const float4 b, const float off) {  
     return make_float4(b.x + off, b.y + off, b.z + off, b.w + off);
 }
 
+// hands image b to the general path: device-side fire-and-forget launch of one CTA of nms_general_kernel (see nms.cuh)
+__device__ __forceinline__ void launch_general_for(const NmsParams &p, const int b) {
+    NmsParams q = p;
+    q.only_image = b;
+    q.all_general = 1;
+    q.prof = nullptr;
+    q.wait_tiles = 0;
+    nms_general_kernel<<<1, kNmsThreads, p.general_smem, cudaStreamFireAndForget>>>(q);
+}
+
 // Register budget of the co-residency (per SM sub-partition: 16384 registers): the score CTA puts 5 of its 18 warps on
 // one sub-partition, this CTA 4 of its 16: 5 * 32 * kScoreRegs + 4 * 32 * kFastRegs <= 16384.
 #ifndef PLYOLO_NMS_REGS
@@ -175,7 +185,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     }
     const bool fast = total <= p.max_nms && gmax <= kFastCapG && (!use_off || (filter_ok && xc <= kMaxCross));
     if (!fast) {
-        if (g == 0 && tid == 0) ctr[kCtrGeneral] = 1;
+        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; launch_general_for(p, b); }
         FAST_EXIT();
     }
 
@@ -452,7 +462,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     FPROF(7);
     if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = nx; prof[14] = g_begin[kGC - 1] + g_cnt[kGC - 1]; }
     if (fb) {  // a pair of different classes suppresses (or a list overflowed): the exact global sweep redoes the image
-        if (g == 0 && tid == 0) ctr[kCtrGeneral] = 1;
+        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; launch_general_for(p, b); }
         FAST_EXIT();
     }
     const int nkept = min(total_k, p.max_det);

@@ -625,6 +625,8 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     np.prof = g_nms_prof;
     const size_t smem = nms_smem_bytes(cap, np.fast_cap, max_det, NT);
     PLYOLO_REQUIRE(smem <= kNmsSmemLimit, "nms working set (%zu B) exceeds shared memory", smem);
+    np.only_image = -1;
+    np.general_smem = (unsigned)smem;
     // the class-split kernel: class-aware NMS, max_det within its kept-key lists, slots within its key layout
     const bool split = variant == PLYOLO_NMS_YOLOX && !class_agnostic && max_det <= kFastMaxDet && A <= (1 << kFastAnchorBits) &&
                        !g_skip_nms;
@@ -643,8 +645,10 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
         }
         count_launch();
     }
-    static const bool no_general = [] { const char *v = getenv("PLYOLO_DEBUG_NO_GENERAL"); return v && v[0] == '1'; }();
-    if (split && no_general) return PLYOLO_OK;  // debug: measures what the (normally idle) general kernel costs
+    if (split) {  // the class-split kernel launches the general path itself, per image, when it has to
+        record_stage_event(2, stream);
+        return PLYOLO_OK;
+    }
     np.wait_tiles = 0;
     np.all_general = split ? 0 : 1;
     np.prof = nullptr;
