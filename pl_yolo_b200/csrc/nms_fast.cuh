@@ -126,6 +126,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     }
     __syncthreads();
     FPROF(1);
+    if (prof && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[13] = (long long)gt; }
     // the last image's cluster keeps the grid alive until the score grid has completed and flushed: whatever follows
     // this kernel in the stream is then ordered after both kernels
     const bool last_image = b == (int)gridDim.y - 1;
@@ -460,7 +461,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     }
     cluster.sync();  // nobody reads another CTA's shared memory past this point (also a CTA barrier)
     FPROF(7);
-    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[12] = nx; prof[14] = g_begin[kGC - 1] + g_cnt[kGC - 1]; }
+    if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[14] = g_begin[kGC - 1] + g_cnt[kGC - 1]; }
     if (fb) {  // a pair of different classes suppresses (or a list overflowed): the exact global sweep redoes the image
         if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; launch_general_for(p, b); }
         FAST_EXIT();
@@ -499,6 +500,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
         if (tid == 0) store_count(p, b, nkept);
     }
     FPROF(8);
+    if (prof && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[15] += 0; prof[12] = (long long)gt; }
     FAST_EXIT();
 #undef FPROF
 #undef FAST_EXIT

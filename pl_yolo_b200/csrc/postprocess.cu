@@ -371,8 +371,15 @@ __global__ void __launch_bounds__(kPpTile) score_kernel_simple(const ScoreParams
 // groups of 128 threads take the tiles round-robin, so the scoring latency of one tile (dependent max
 // chains, barriers, the bucket atomics) overlaps the next tiles' loads and compute.
 constexpr int kStages = 4;
-constexpr int kConsumers = 4;
-constexpr int kProducers = 2;  // producer warps (FUSED: each copies half of the channel rows)
+#ifndef PLYOLO_SCORE_CONSUMERS
+#define PLYOLO_SCORE_CONSUMERS 4
+#endif
+#ifndef PLYOLO_SCORE_PRODUCERS
+#define PLYOLO_SCORE_PRODUCERS 2
+#endif
+constexpr int kConsumers = PLYOLO_SCORE_CONSUMERS;
+static_assert(kConsumers == kStages, "only the 4-group / 4-stage layout is validated (3 groups fault, 1 producer warp gains nothing)");
+constexpr int kProducers = PLYOLO_SCORE_PRODUCERS;  // producer warps (cp.async fallback: each copies part of the channel rows)
 constexpr int kScoreThreads = 32 * kProducers + kPpTile * kConsumers;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {

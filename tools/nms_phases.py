@@ -34,6 +34,13 @@ print("  %-22s %7.2f %7.2f" % ("  warp 0 in warp_sort", us(p[done, 15]).mean(), 
 work = p[done, 8] - p[done, 1]
 print("  %-22s %7.2f %7.2f" % ("after the tiles", us(work).mean(), us(work).max()))
 print("n per group (max %d)" % p[:, 10].max(), p[:, 10].reshape(B, G)[:8].tolist())
-print("kept per group (max %d), cross boxes after the filter (max %d), survivors of the rounds per group: mean %.0f max %d (of n mean %.0f)" % (p[:, 11].max(), p[:, 12].max(), p[:, 14].mean(), p[:, 14].max(), p[:, 10].mean()))
+print("kept per group (max %d), survivors of the rounds per group: mean %.0f max %d (of n mean %.0f)" % (p[:, 11].max(), p[:, 14].mean(), p[:, 14].max(), p[:, 10].mean()))
+# absolute timeline (globaltimer, ns): when each image's tiles were complete and when its NMS was done
+t_flag = p[:, 13].reshape(B, G).min(1).astype(np.float64)
+t_end = p[:, 12].reshape(B, G).max(1).astype(np.float64)
+t0 = t_flag.min()
+print("image: tiles complete at / NMS done at (us after the first image's tiles were complete)")
+print("  " + "  ".join("%d: %.1f/%.1f" % (b, (t_flag[b] - t0) / 1e3, (t_end[b] - t0) / 1e3) for b in range(0, B, max(1, B // 16))))
+print("  last image's tiles complete at %.1f us; last NMS done at %.1f us -> exposed tail %.1f us" % ((t_flag.max() - t0) / 1e3, (t_end.max() - t0) / 1e3, (t_end.max() - t_flag.max()) / 1e3))
 print("ncross", ctr[:, 5].tolist())
 print("general-path flags", ctr[:, 6].tolist(), "tiles done", ctr[:, 7].tolist()[:4])
