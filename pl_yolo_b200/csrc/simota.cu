@@ -31,7 +31,10 @@
 namespace plyolo {
 
 constexpr int kPrepThreads = 512;
-constexpr int kPrepSplit = 4;     // CTAs per image in the prep kernel
+#ifndef PLYOLO_PREP_SPLIT
+#define PLYOLO_PREP_SPLIT 4
+#endif
+constexpr int kPrepSplit = PLYOLO_PREP_SPLIT;  // CTAs per image in the prep kernel
 constexpr int kGtPerCta = 8;      // GTs per CTA in the match kernel
 constexpr int kMatchWarps = 16;  // two per GT during the IoU sweep
 constexpr int kMatchThreads = kMatchWarps * 32;
