@@ -370,7 +370,11 @@ def main():
         # joins at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
         # step would cost more than the 48 us of device work) out of the measurement.
         round_graph = None
-        R_STEPS = n_sets * (4 if (xch or pdx) else 1)  # steps per round (one fence / one exposed all-gather per round)
+        # steps per round (one fence / one exposed exchange per round): up to 8 passes over the input sets, dividing `steps`
+        mult = 1
+        if xch or pdx:
+            mult = max([m for m in range(1, 9) if steps % (n_sets * m) == 0] or [4])
+        R_STEPS = n_sets * mult
         if graphs is not None:
             try:
                 with torch.cuda.stream(stream):
@@ -488,7 +492,7 @@ def main():
     sim["workload"] = "YOLOX-s SimOTA assignment batch 32, G~U{1..120} (mean %.1f) [BASELINE configs[2]]" % sim["gt_mean"]
 
     extra = {}
-    Ke = max(10, min(K, 30))
+    Ke = 32 if K >= 32 else max(8, (K // 8) * 8)  # steps of the extra configurations (whole rounds)
     if not args.skip_extra:
         # SimOTA with COCO-like small objects: 15 % of the GTs are 2-8 px (fewer in-both anchors than the dynamic k)
         try:
