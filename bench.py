@@ -235,6 +235,7 @@ def main():
             os.environ.setdefault("PLYOLO_SCORE_SMS_RESERVED", "2")
     from pl_yolo_b200 import YOLOXLoss, _lib, ops, postprocess_dense
     from pl_yolo_b200.distributed import DetectionExchange, PeerDetections, fused_det_buffer, shard_range
+    from pl_yolo_b200.pipeline import Lanes, default_depth
     peer_tables = []
 
     K, W = args.steps, args.warmup
@@ -365,21 +366,36 @@ def main():
                 xch.submit(s, bufs[s][0], gbufs[s])
 
         graphs, lpg = capture(eager, n_sets)
-        # One graph per ROUND of n_sets steps: every step's kernels, and (N > 1) every step's all-gather forked onto the
-        # side stream right behind its NMS kernel, so that it runs under the next step's score kernel; the side stream
-        # joins at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
-        # step would cost more than the 48 us of device work) out of the measurement.
+        # Batches in flight (pl_yolo_b200.pipeline): step i runs on lane i % depth — its own stream, scratch and output
+        # slot — so that the NMS tail of one batch runs under the score kernel of the next ones.  depth divides n_sets:
+        # an output slot always belongs to the same lane, i.e. its reuse is ordered by that lane's stream.
+        depth = int(os.environ.get("BENCH_IN_FLIGHT", "0")) or default_depth(b_loc)
+        depth = max(d for d in range(1, min(depth, n_sets) + 1) if n_sets % d == 0)
+        lanes = Lanes(depth, dev) if depth > 1 else None
+
+        def issue_steps(first, n):
+            """steps first .. first+n-1 on their lanes, joined back into the current stream"""
+            if lanes is None:
+                for i in range(first, first + n):
+                    step_eager(i % n_sets)
+                return
+            lanes.fork()
+            for i in range(first, first + n):
+                lanes.issue(i, lambda i=i: step_eager(i % n_sets))
+            lanes.join()
+
+        # One graph per ROUND of R_STEPS steps: every step's kernels on its lane, and (N > 1) every step's exchange forked
+        # onto the side stream right behind its NMS kernel, so that it runs under the following steps; lanes and side
+        # stream join at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
+        # step would cost more than the device work of a step) out of the measurement.
         round_graph = None
-        # steps per round (one fence / one exposed exchange per round): up to 8 passes over the input sets, dividing `steps`
-        mult = 1
-        if xch or pdx:
-            mult = max([m for m in range(1, 9) if steps % (n_sets * m) == 0] or [4])
+        # steps per round (one join / one fence per round): up to 8 passes over the input sets, dividing `steps`
+        mult = max([m for m in range(1, 9) if steps % (n_sets * m) == 0] or [1])
         R_STEPS = n_sets * mult
         if graphs is not None:
             try:
                 with torch.cuda.stream(stream):
-                    for s in range(n_sets):
-                        step_eager(s)
+                    issue_steps(0, n_sets)
                     if xch:
                         xch.finish()
                     fence()
@@ -388,8 +404,7 @@ def main():
                         xch.done = [None] * n_sets
                     round_graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(round_graph, stream=stream):
-                        for s in range(R_STEPS):
-                            step_eager(s % n_sets)
+                        issue_steps(0, R_STEPS)
                         if xch:
                             xch.finish()
                         fence()
@@ -398,7 +413,7 @@ def main():
                     round_graph.replay()
                     torch.cuda.synchronize(dev)
             except Exception as e:  # noqa: BLE001
-                sys.stderr.write("round graph capture failed (%r): stepping graph by graph\n" % (e,))
+                sys.stderr.write("round graph capture failed (%r): stepping eagerly\n" % (e,))
                 round_graph = None
                 torch.cuda.synchronize(dev)
                 if xch:
@@ -411,11 +426,9 @@ def main():
                     round_graph.replay()
                     i += R_STEPS
                     continue
-                if graphs is not None and not xch:
-                    graphs[i % n_sets].replay()
-                else:
-                    step_eager(i % n_sets)
-                i += 1
+                m = min(n - i, n_sets - i % n_sets)  # eager remainder: at most one pass over the input sets at a time
+                issue_steps(i, m)
+                i += m
 
         def finish():
             if xch:
@@ -442,9 +455,15 @@ def main():
         ms2, _, _ = timed(lambda i: g2[i % n_sets].replay() if g2 is not None else eager(i % n_sets), min(steps, 40))
         L.plyolo_debug_skip_nms(0)
         score_s = ms2 * 1e-3 / min(steps, 40)
+        # one batch in flight: the latency of a step (the same kernels, one stream)
+        one_us = None
+        if graphs is not None:
+            ms1, _, _ = timed(lambda i: graphs[i % n_sets].replay(), min(steps, 40), clocks=False)
+            one_us = 1e3 * ms1 / min(steps, 40)
         return {"value": world * b_loc * steps / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms / steps, "batch_per_gpu": b_loc,
                 "anchors": anchors_of(size), "gpu_launches": int(launches),
-                "launch": ("cuda_graph (one replay per round of %d steps)" % R_STEPS) if round_graph is not None else ("cuda_graph" if graphs is not None else "eager"),
+                "batches_in_flight": depth, "one_in_flight_step_us": one_us,
+                "launch": ("cuda_graph (one replay per round of %d steps, %d batches in flight)" % (R_STEPS, depth)) if round_graph is not None else "eager",
                 "dets_per_image": float(torch.stack([b[2] for b in bufs]).float().mean()),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "algorithmic_bytes_per_image": bytes_decode_nms(size),
@@ -507,7 +526,8 @@ def main():
         try:
             h1 = [[t[:1].contiguous() for t in hs] for hs in heads]
             r = bench_decode_nms(h1, 1, SIZE, Ke, exchange=False)
-            extra["cfg1"] = {"workload": "YOLOX-s 640x640 batch 1 decode + postprocess [BASELINE configs[0]]", "latency_us": 1e3 * r["ms_per_step"],
+            extra["cfg1"] = {"workload": "YOLOX-s 640x640 batch 1 decode + postprocess [BASELINE configs[0]]", "latency_us": r["one_in_flight_step_us"],
+                             "us_per_image_pipelined": 1e3 * r["ms_per_step"], "batches_in_flight": r["batches_in_flight"],
                              "value": r["value"] / world, "unit": "img/s (one GPU)", "dets_per_image": r["dets_per_image"],
                              "score_stage_us": r["roofline"]["score_stage"]["us"]}
             del h1
@@ -524,7 +544,8 @@ def main():
             s4 = bench_simota(h4, l4, b4, SIZE, Ke)
             extra["cfg4"] = {"workload": "YOLOX-l 640x640 batch 256 sharded by image over %d GPU(s): decode+NMS (+ detection all-gather "
                                          "every step) and SimOTA [BASELINE configs[3]]" % world, "scaling": "strong", "batch_per_gpu": b4,
-                             "decode_nms": {"value": r["value"], "unit": "img/s", "ms_per_step": r["ms_per_step"], "frac": r["roofline"]["frac"] * world,
+                             "decode_nms": {"value": r["value"], "unit": "img/s", "ms_per_step": r["ms_per_step"], "batches_in_flight": r["batches_in_flight"],
+                                            "one_in_flight_step_us": r["one_in_flight_step_us"], "frac": r["roofline"]["frac"] * world,
                                             "frac_note": "whole job against N x the measured HBM peak" if world > 1 else "against the measured HBM peak"},
                              "simota": {"value": s4["value"], "unit": "img/s", "ms_per_step": s4["ms_per_step"]}}
             extra["cfg4"]["decode_nms"]["frac"] = r["roofline"]["frac"]
@@ -542,6 +563,7 @@ def main():
             extra["cfg5"] = {"workload": "YOLOX-x 1280x1280 (33600 anchors) 8 images per GPU, 250-500 GT per image [BASELINE configs[4]]",
                              "batch_per_gpu": 8,
                              "decode_nms": {"value": r["value"], "unit": "img/s", "ms_per_step": r["ms_per_step"], "frac": r["roofline"]["frac"],
+                                            "batches_in_flight": r["batches_in_flight"], "one_in_flight_step_us": r["one_in_flight_step_us"],
                                             "dets_per_image": r["dets_per_image"],
                                             "note": "~16 k candidates per image: max_nms = 10000 truncates by position, every image takes the general NMS path"},
                              "simota": {"value": s5["value"], "unit": "img/s", "ms_per_step": s5["ms_per_step"], "gt_mean": s5["gt_mean"],
@@ -661,12 +683,14 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "anchors": anchors_of(SIZE), "classes": C,
                        "dets_per_image": dn["dets_per_image"], "launch": dn["launch"], "l2": "4 input sets rotated (366 MB > 126 MB L2)",
+                       "batches_in_flight": dn["batches_in_flight"],
                        "exchange": "per step: " + dn["exchange"]},
             "roofline": {"bound": "hbm", "achieved": roof["achieved"], "peak": peak, "unit": "GB/s", "frac": roof["frac"],
                          "traffic": (traffic_bytes("score_kernel") or 0) + (traffic_bytes("nms_fast_kernel") or 0) or None,
                          "peak_source": peak_src,
-                         "kernel": "whole step: memset + score_kernel<fused> (HBM stream) with nms_fast_kernel running under it + nms_general_kernel",
-                         "step_us": 1e3 * dn["ms_per_step"], "algorithmic_bytes_per_launch": BATCH * bytes_decode_nms(SIZE),
+                         "kernel": "whole step: memset + score_kernel<fused> (HBM stream) with nms_fast_kernel running under it (and under the "
+                                   "following batches' score kernels: %d batches in flight, one stream each)" % dn["batches_in_flight"],
+                         "step_us": 1e3 * dn["ms_per_step"], "one_in_flight_step_us": dn["one_in_flight_step_us"], "algorithmic_bytes_per_launch": BATCH * bytes_decode_nms(SIZE),
                          "algorithmic_bytes_per_image": bytes_decode_nms(SIZE), "score_stage": roof["score_stage"]},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Kx,
                     "api": "postprocess_dense(YOLOXLoss(lazy_eval=True).eval()(heads, None), 0.01, 0.65)",

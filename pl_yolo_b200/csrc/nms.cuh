@@ -110,6 +110,7 @@ struct NmsParams {
     int only_image;   // nms_general_kernel launched from the device for ONE image (>= 0), else -1: one CTA per image
     unsigned general_smem;  // dynamic shared memory of nms_general_kernel (for the device-side launch)
     int all_general;  // nms_general_kernel: every image takes the general path (no class-split kernel ran)
+    int device_launch;  // the class-split kernel launches the general path itself (0: the host launched it behind it)
     int wait_tiles;   // nms_fast_kernel: spin on the image's scored-tile counter (the score kernel may still be running)
     float thr_f;
     double thr_d;
@@ -878,12 +879,16 @@ constexpr int kTeamMin = 192;  // classes with more candidates are sorted by a t
 
 // ---- general path: one CTA per image that needs it ------------------------------------------------------
 // An image is redone here, exactly, when the class-split kernel (nms_fast.cuh) finds that it cannot handle it
-// (max_nms truncation, a class group above its capacity, a cross-class pair that suppresses, list overflows): that
-// kernel then launches this one FROM THE DEVICE for the one image (CUDA dynamic parallelism, fire-and-forget: the images
-// that need it run side by side, and the stream does not move on before they have finished) — an idle launch of 1024-thread /
-// 180 KB CTAs from the host costs 8.6 us per step (measured), so the host only launches it when the call as a whole
-// cannot use the class split (`all_general`: class-agnostic NMS, the YOLOv3 / YOLOv5 call sites, very large max_det,
-// anchors beyond the fast key layout).
+// (max_nms truncation, a class group above its capacity, a cross-class pair that suppresses, list overflows).
+//  * Plain stream launches: that kernel launches this one FROM THE DEVICE for the one image (CUDA dynamic parallelism,
+//    fire-and-forget: the images that need it run side by side, and the stream does not move on before they have
+//    finished) — nothing at all is launched for the normal step.
+//  * Under stream capture (CUDA graphs) the host launches it behind the class-split kernel, one CTA per image, each
+//    leaving at once unless its image was flagged: fire-and-forget children of a graph's kernel node are NOT ordered
+//    before the rest of the graph / the next replay (measured: a replayed step "finished" in 60 us and its rows arrived
+//    several replays later), so device-side launches are not used there.
+//  * The host also launches it when the call as a whole cannot use the class split (`all_general`: class-agnostic NMS,
+//    the YOLOv3 / YOLOv5 call sites, very large max_det, anchors beyond the fast key layout).
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_general_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     // programmatic dependent launch: the CTAs may be scheduled while the previous kernel drains; everything below

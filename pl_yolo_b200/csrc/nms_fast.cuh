@@ -27,11 +27,7 @@
 
 namespace plyolo {
 
-constexpr int kFastThreads = 512;
-constexpr int kFastWarps = kFastThreads / 32;
-constexpr int kFastPer = 3;                           // candidates per thread
-constexpr int kFastCapG = kFastThreads * kFastPer;    // 1536 candidates per (image, class group)
-constexpr int kGC = kMaxClasses / kGroups;            // class slots per group: class c -> slot c / kGroups
+constexpr int kGC = 32;                               // arrays over class slots (>= kGCn)
 #ifndef PLYOLO_NMS_ROUNDS
 #define PLYOLO_NMS_ROUNDS 4
 #endif
@@ -39,17 +35,29 @@ constexpr int kFastRounds = PLYOLO_NMS_ROUNDS;        // max-first rounds before
 constexpr int kFastCross = 128;                       // cross boxes that can suppress across classes (after the filters)
 constexpr int kAllKeys = 960;                         // kept keys of all groups in the merge
 constexpr int kKeys2Cap = 640;                        // kept keys of one group (more -> general path)
-constexpr int kIdxBits = 11;                          // box index inside the group (kFastCapG <= 2048)
+constexpr int kIdxBits = 11;                          // box index inside the group (cap <= 2048)
 constexpr int kFastAnchorBits = 21;                   // anchor index must fit (A <= 2 097 152)
 constexpr unsigned long long kIdxMask = (1ull << kIdxBits) - 1ull;
 constexpr size_t kFastUnion = (size_t)(kAllKeys + 64) * 8;  // cross list | kept index lists | merged key list
-static_assert(kFastUnion >= (size_t)kFastCapG * 2 && kFastUnion >= (size_t)kFastCross * 24, "union region too small");
-static_assert(kFastCapG <= (1 << kIdxBits) && kGroups == 4 && kGC == 32, "layout assumptions");
-
-// dynamic shared memory: skey[cap] u64 | sbox[cap] float4 | scls[cap] u8 | union | keys2[kKeys2Cap] u64 |
-// kidx2[kKeys2Cap] u16  (55 KB with the static part: fits on an SM beside the score CTA's 171.5 KB)
-constexpr size_t kFastSmemBytes = (size_t)kFastCapG * 25 + kFastUnion + (size_t)kKeys2Cap * 10;
+static_assert(kFastUnion >= (size_t)1536 * 2 && kFastUnion >= (size_t)kFastCross * 24, "union region too small");
 constexpr int kFastMaxDet = kKeys2Cap - 32;  // max_det the fast kernel supports
+
+// One image = one cluster of NG class-group CTAs.  Two layouts share the code below:
+//   NG = 4: 512 threads x 3 candidates (1536 per group), 48 registers — the layout in use;
+//   NG = 8: 256 threads x 4 candidates (1024 per group), 64 registers — experiment (PLYOLO_NMS_GROUPS=8, see
+//           nms_groups_for in postprocess.cu: exact, not faster).
+template <int NG>
+struct FastCfg {
+    static_assert(NG == 4 || NG == 8, "4 or 8 class groups per image");
+    static constexpr int kThreads = 2048 / NG;
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kPer = NG == 4 ? 3 : 4;           // candidates per thread
+    static constexpr int kCap = kThreads * kPer;           // candidates per (image, class group)
+    static constexpr int kGCn = kMaxClasses / NG;          // class slots per group: class c -> slot c / NG
+    static constexpr int kRegs = NG == 4 ? 48 : 64;
+    static constexpr int kXPer = kMaxCross / kThreads;     // cross-list entries per thread
+    static constexpr size_t kSmem = (size_t)kCap * 25 + kFastUnion + (size_t)kKeys2Cap * 10;
+};
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
@@ -76,13 +84,11 @@ __device__ __forceinline__ void launch_general_for(const NmsParams &p, const int
 }
 
 // Register budget of the co-residency (per SM sub-partition: 16384 registers): the score CTA puts 5 of its 18 warps on
-// one sub-partition, this CTA 4 of its 16: 5 * 32 * kScoreRegs + 4 * 32 * kFastRegs <= 16384.
-#ifndef PLYOLO_NMS_REGS
-#define PLYOLO_NMS_REGS 48
-#endif
-constexpr int kFastRegs = PLYOLO_NMS_REGS;
-
-__global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_kernel(const NmsParams p) {
+// one sub-partition, this CTA 4 of its 16 (NG = 4) or 2 of its 8 (NG = 8): 5 * 32 * kScoreRegs + 4 * 32 * 48 <= 16384.
+template <int NG>
+__global__ void __cluster_dims__(NG, 1, 1) __maxnreg__(FastCfg<NG>::kRegs) nms_fast_kernel(const NmsParams p) {
+    constexpr int kGroups = NG, kFastThreads = FastCfg<NG>::kThreads, kFastPer = FastCfg<NG>::kPer;
+    constexpr int kFastCapG = FastCfg<NG>::kCap, kGCn = FastCfg<NG>::kGCn, kXPer = FastCfg<NG>::kXPer;
     extern __shared__ __align__(16) unsigned char fsm[];
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(fsm);                       // [cap] class segments
     float4 *sbox = reinterpret_cast<float4 *>(fsm + (size_t)kFastCapG * 8);                        // [cap] by box index, un-offset
@@ -113,12 +119,12 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     FPROF(0);
 
     // ---- wait until every tile of the image has been scored (the score kernel may still be running)
-    if (tid < kGC) {
+    if (tid < kGC) {  // (slots >= kGCn stay empty)
 #pragma unroll
         for (int r = 0; r < kFastRounds; ++r) { c_best_hi[r][tid] = 0xffffffffu; c_best_lo[r][tid] = 0xffffffffu; }
         g_cnt[tid] = 0;
     }
-    if (tid < kMaxClasses) { x_minx[tid] = 0xffffffffu; x_miny[tid] = 0xffffffffu; }
+    for (int i = tid; i < kMaxClasses; i += kFastThreads) { x_minx[i] = 0xffffffffu; x_miny[i] = 0xffffffffu; }
     if (tid == 0) {
         g_next = 0; g_fallback = 0; g_nk2 = 0; g_nx = 0;
         if (p.wait_tiles)
@@ -134,13 +140,13 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
 
     // the bucket is read before its fill count is known (entries past the count are stale bytes of the caller-owned
     // workspace, never used): one L2 round trip for counters, keys and boxes instead of two
-    const unsigned long long *bucket = p.ws.gkey + ((size_t)b * kGroups + g) * kFastCapG;
-    const float4 *bbox = p.ws.gbox + ((size_t)b * kGroups + g) * kFastCapG;
+    const unsigned long long *bucket = p.ws.gkey + (size_t)b * kBucketImg + g * (kBucketImg / kGroups);
+    const float4 *bbox = p.ws.gbox + (size_t)b * kBucketImg + g * (kBucketImg / kGroups);
     unsigned long long nk[kFastPer];
     int cl[kFastPer];
-    float4 xb_spec;
-    unsigned long long xk_spec;
-    static_assert(kMaxCross == kFastThreads, "one cross-list entry per thread");
+    float4 xb_spec[kXPer];
+    unsigned long long xk_spec[kXPer];
+    static_assert(kXPer * kFastThreads == kMaxCross, "the cross list is read kXPer entries per thread");
     {
         unsigned long long key[kFastPer];
         float4 bx[kFastPer];
@@ -149,8 +155,11 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
             key[k] = __ldcg(bucket + tid + k * kFastThreads);
             bx[k] = __ldcg(bbox + tid + k * kFastThreads);
         }
-        xb_spec = __ldcg(p.ws.xbox + (size_t)b * kMaxCross + tid);  // kMaxCross == kFastThreads entries per image
-        xk_spec = __ldcg(p.ws.xkey + (size_t)b * kMaxCross + tid);
+#pragma unroll
+        for (int e = 0; e < kXPer; ++e) {
+            xb_spec[e] = __ldcg(p.ws.xbox + (size_t)b * kMaxCross + tid + e * kFastThreads);
+            xk_spec[e] = __ldcg(p.ws.xkey + (size_t)b * kMaxCross + tid + e * kFastThreads);
+        }
 #pragma unroll
         for (int k = 0; k < kFastPer; ++k) {  // meaningless past the fill count: never used there
             const int i = tid + k * kFastThreads;
@@ -168,9 +177,9 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
         gmax = max(gmax, c);
         if (q == g) n = c;
     }
-    const int xc = __ldcg(&ctr[kGroups + 1]);
+    const int xc = __ldcg(&ctr[kCtrCross]);
     const float max_x2 = ordered_float((unsigned)__ldcg(&ctr[kCtrMaxX2])), max_y2 = ordered_float((unsigned)__ldcg(&ctr[kCtrMaxY2]));
-    const float span = ordered_float((unsigned)__ldcg(&ctr[kGroups])) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
+    const float span = ordered_float((unsigned)__ldcg(&ctr[kCtrMaxCoord])) + 1.0f;  // max_coordinate + 1 (tv:ops/boxes.py:100)
     const bool per_class = 4 * (long long)total > ((p.flavor & PLYOLO_NMS_RULE_CPU) ? 4000 : 100000);  // tv:ops/boxes.py:80
     const bool use_off = !per_class;
     const bool filter_ok = span > 0.f && span * 256.f < 4.0e6f;
@@ -186,7 +195,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     }
     const bool fast = total <= p.max_nms && gmax <= kFastCapG && (!use_off || (filter_ok && xc <= kMaxCross));
     if (!fast) {
-        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; launch_general_for(p, b); }
+        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; if (p.device_launch) launch_general_for(p, b); }
         FAST_EXIT();
     }
 
@@ -197,25 +206,28 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     // neither suppress nor be suppressed across classes.  Real boxes never pass (most of the box would have to lie
     // beyond the far corner of every other box), so the list is normally empty and the check below costs nothing.
     const bool xcheck = use_off && xc > 0;
-    if (xcheck && tid < xc) {
-        const float4 x = xb_spec;
-        const float wmax = (max_x2 - span + 1.0f) - x.x;
-        const float hmax = (max_y2 - span + 1.0f) - x.y;
-        const float a_lo = fmaxf((x.z - x.x) - 1.0f, 0.f) * fmaxf((x.w - x.y) - 1.0f, 0.f) * 0.99999f;
-        const bool drop = !(wmax > 0.f && hmax > 0.f) || (p.thr_f > 0.f && (wmax * hmax) * 1.00001f < p.thr_f * a_lo);
-        if (!drop) {
-            const unsigned long long kx = xk_spec;
-            const int xi = atomicAdd(&g_nx, 1);
-            if (xi < kFastCross) {
-                atomicMin(&x_minx[key_class(kx)], float_ordered(x.x));
-                atomicMin(&x_miny[key_class(kx)], float_ordered(x.y));
-                x_box[xi] = shift_box(x, (float)key_class(kx) * span);
-                x_key[xi] = kx;
+    if (xcheck) {
+#pragma unroll
+        for (int e = 0; e < kXPer; ++e) {
+            if (tid + e * kFastThreads >= xc) continue;
+            const float4 x = xb_spec[e];
+            const float wmax = (max_x2 - span + 1.0f) - x.x;
+            const float hmax = (max_y2 - span + 1.0f) - x.y;
+            const float a_lo = fmaxf((x.z - x.x) - 1.0f, 0.f) * fmaxf((x.w - x.y) - 1.0f, 0.f) * 0.99999f;
+            const bool drop = !(wmax > 0.f && hmax > 0.f) || (p.thr_f > 0.f && (wmax * hmax) * 1.00001f < p.thr_f * a_lo);
+            if (!drop) {
+                const unsigned long long kx = xk_spec[e];
+                const int xi = atomicAdd(&g_nx, 1);
+                if (xi < kFastCross) {
+                    atomicMin(&x_minx[key_class(kx)], float_ordered(x.x));
+                    atomicMin(&x_miny[key_class(kx)], float_ordered(x.y));
+                    x_box[xi] = shift_box(x, (float)key_class(kx) * span);
+                    x_key[xi] = kx;
+                }
             }
         }
     }
 
-    FPROF(9);
     // ---- 2. max-first rounds.  live bit k: candidate k of this thread may still be kept; win bit k: it won a round
     unsigned live = 0u, win = 0u;
 #pragma unroll
@@ -463,7 +475,7 @@ __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_
     FPROF(7);
     if (prof && tid == 0) { prof[10] = n; prof[11] = Kg; prof[14] = g_begin[kGC - 1] + g_cnt[kGC - 1]; }
     if (fb) {  // a pair of different classes suppresses (or a list overflowed): the exact global sweep redoes the image
-        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; launch_general_for(p, b); }
+        if (g == 0 && tid == 0) { ctr[kCtrGeneral] = 1; if (p.device_launch) launch_general_for(p, b); }
         FAST_EXIT();
     }
     const int nkept = min(total_k, p.max_det);

@@ -28,15 +28,18 @@
 namespace plyolo {
 
 constexpr int kPpTile = 128;
-constexpr int kGroups = 4;      // class groups per image (class & 3): one NMS CTA each
+constexpr int kMaxGroups = 8;    // class groups per image: 4 (class & 3) or 8 (class & 7), one NMS CTA each (ScoreParams::ng)
 constexpr int kMaxCross = 512;  // boxes that may reach into another class's offset range (x1, y1 < -0.5)
 constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
 constexpr int kImgCtr = 16;     // ints per image in the counter block (zeroed before every call)
-constexpr int kCtrGeneral = 6;  // counter block: the image must be redone by the general path
-constexpr int kCtrDone = 7;     // counter block: tiles of the image that have been scored (released by the score kernel)
-constexpr int kCtrMaxX2 = 8;    // counter block: largest x2 / y2 of the image's candidates (ordered uint): bounds which
-constexpr int kCtrMaxY2 = 9;    //   cross boxes can reach another class's offset range at all
-constexpr int kBucketCap = 1536;  // bucket entries kept per (image, class group) == kFastCapG of nms_fast.cuh
+// counter block of an image: [0, kMaxGroups) candidates per class group, then
+constexpr int kCtrMaxCoord = 8;  // largest coordinate (ordered uint): tv:ops/boxes.py:99
+constexpr int kCtrCross = 9;     // boxes listed in the cross list
+constexpr int kCtrGeneral = 10;  // the image must be redone by the general path
+constexpr int kCtrDone = 11;     // tiles of the image that have been scored (released by the score kernel)
+constexpr int kCtrMaxX2 = 12;    // largest x2 / y2 of the image's candidates (ordered uint): bounds which cross boxes
+constexpr int kCtrMaxY2 = 13;    //   can reach another class's offset range at all
+constexpr int kBucketImg = 8192; // bucket entries per image: ng groups of kBucketImg / ng (the NMS kernels stage 1536 / 1024 of them)
 
 constexpr size_t kNmsSmemLimit = 190 * 1024;  // dynamic shared memory of the NMS kernels (33 KB are static)
 struct CandWs {
@@ -46,9 +49,9 @@ struct CandWs {
     int *meta;          // [B, NT*128]  anchor | class << 24
     float *aux;         // [B, NT*128]  second score of the YOLOv3 / YOLOv5 call sites (objectness / best class score)
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
-    int *ctr;                     // [B, kImgCtr]  gcount[kGroups] | max coordinate (ordered uint) | #cross | general | tiles done | max x2 | max y2
-    unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | anchor
-    float4 *gbox;                 // [B, kGroups, kBucketCap]  the same candidates' corners
+    int *ctr;                     // [B, kImgCtr]  counter block (kCtr*)
+    unsigned long long *gkey;     // [B, ng, kBucketImg / ng]  class << 57 | ~ordered(score) << 25 | anchor
+    float4 *gbox;                 // [B, ng, kBucketImg / ng]  the same candidates' corners
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
 };
@@ -59,6 +62,7 @@ struct ScoreParams {
     int B, A, C, ch, NT;
     float conf_thr;
     int bulk_ok;
+    int ng;       // class groups per image (4 or 8): which NMS kernel follows
     int variant;  // PLYOLO_NMS_YOLOX / _YOLOV3 / _YOLOV5: which reference call site's filter + score arithmetic (preds input only)
     CandWs ws;
     long long *prof;  // debug: [gridDim.x][kConsumers][8] accumulated cycles per consumer phase, or null
@@ -67,8 +71,8 @@ struct ScoreParams {
 // per consumer group (128 threads = one tile at a time) scratch
 struct TileShared {
     int warp_cnt[kPpTile / 32];
-    int g_wcnt[kPpTile / 32][kGroups];
-    int g_base[kGroups];
+    unsigned char g_wcnt[kPpTile / 32][kMaxGroups];  // per-warp ballots' popcounts (<= 32)
+    int g_base[kMaxGroups];
     float w_max[kPpTile / 32], w_maxz[kPpTile / 32], w_maxw[kPpTile / 32];
 };
 
@@ -271,10 +275,11 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (lane == 0) sh.warp_cnt[warp] = __popc(m);
     // class-group ballots and the tile's max coordinate ride on the same barrier
-    const int grp = cls & (kGroups - 1);
+    const int grp = cls & (p.ng - 1);
     unsigned gm = 0u;
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
+    for (int g = 0; g < kMaxGroups; ++g) {
+        if (g >= p.ng) break;  // uniform
         const unsigned mg = __ballot_sync(0xffffffffu, pass && grp == g);
         if (lane == 0) sh.g_wcnt[warp][g] = __popc(mg);
         if (grp == g) gm = mg;
@@ -310,7 +315,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     // image's max coordinate (tv:ops/boxes.py:99) and the boxes that can reach another class's offset range
     if (total == 0) return;  // uniform for the group
     int *ctr = p.ws.ctr + b * kImgCtr;
-    if (tid < kGroups) {
+    if (tid < p.ng) {
         int n = 0;
 #pragma unroll
         for (int w = 0; w < kPpTile / 32; ++w) n += sh.g_wcnt[w][tid];
@@ -320,7 +325,7 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         float mx = wm[0];
 #pragma unroll
         for (int w = 1; w < kPpTile / 32; ++w) mx = fmaxf(mx, wm[w]);
-        atomicMax(reinterpret_cast<unsigned *>(&ctr[tid == 32 ? kGroups : (tid == 33 ? kCtrMaxX2 : kCtrMaxY2)]), float_ordered(mx));
+        atomicMax(reinterpret_cast<unsigned *>(&ctr[tid == 32 ? kCtrMaxCoord : (tid == 33 ? kCtrMaxX2 : kCtrMaxY2)]), float_ordered(mx));
     }
     group_barrier(bar_id);
     TPROF(5);
@@ -330,12 +335,13 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
         // the low bits order equal scores by anchor (ascending anchor == the reference's candidate order)
         const unsigned long long key = ((unsigned long long)cls << 57) |
                                        ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)(tc.anchor_base + src_t);
-        if (pos < kBucketCap) {  // a fuller group is redone by the general path from the slot arrays
-            p.ws.gkey[((size_t)b * kGroups + grp) * kBucketCap + pos] = key;
-            p.ws.gbox[((size_t)b * kGroups + grp) * kBucketCap + pos] = box;
+        const int gcap = kBucketImg / p.ng;
+        if (pos < gcap) {  // a fuller group is redone by the general path from the slot arrays
+            p.ws.gkey[(size_t)b * kBucketImg + grp * gcap + pos] = key;
+            p.ws.gbox[(size_t)b * kBucketImg + grp * gcap + pos] = box;
         }
         if (box.x < -0.5f && box.y < -0.5f) {
-            const int xi = atomicAdd(&ctr[kGroups + 1], 1);
+            const int xi = atomicAdd(&ctr[kCtrCross], 1);
             if (xi < kMaxCross) {
                 p.ws.xkey[(size_t)b * kMaxCross + xi] = key;
                 p.ws.xbox[(size_t)b * kMaxCross + xi] = box;
@@ -435,8 +441,18 @@ score_kernel(const ScoreParams p, const __grid_constant__ TmapPack tmaps, const 
     extern __shared__ __align__(128) float stages[];  // [kStages][ch * 128]
     // programmatic dependent launch: the NMS grid may be scheduled from now on (its clusters wait for their image)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
-    __shared__ TileShared sh[kConsumers];
+    // Static shared memory comes first in the CTA's window and the dynamic part follows it with 16-byte alignment only
+    // (the __align__ on an extern array is not honoured across the two): the tensor copies need their stage 128-byte
+    // aligned, so the static part is one struct whose size is a multiple of 128 (checked below, trap if it ever moves).
+    struct alignas(128) ScoreStatic {
+        uint64_t full_bar[kStages], empty_bar[kStages];
+        TileShared sh[kConsumers];
+    };
+    static_assert(sizeof(ScoreStatic) % 128 == 0, "dynamic shared memory must start 128-byte aligned");
+    __shared__ ScoreStatic st;
+    uint64_t *const full_bar = st.full_bar, *const empty_bar = st.empty_bar;
+    TileShared *const sh = st.sh;
+    if (threadIdx.x == 0 && (smem_u32(stages) & 127u)) __trap();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stage_floats = p.ch * kPpTile;
     const int total = p.NT * p.B;
@@ -536,8 +552,8 @@ static size_t cand_ws_layout(int B, int NT, CandWs *ws, unsigned char *base) {
     size_t o_sc = take(slots * sizeof(float));
     size_t o_meta = take(slots * sizeof(int));
     size_t o_aux = take(slots * sizeof(float));
-    size_t o_gkey = take((size_t)B * kGroups * kBucketCap * sizeof(unsigned long long));
-    size_t o_gbox = take((size_t)B * kGroups * kBucketCap * sizeof(float4));
+    size_t o_gkey = take((size_t)B * kBucketImg * sizeof(unsigned long long));
+    size_t o_gbox = take((size_t)B * kBucketImg * sizeof(float4));
     size_t o_xkey = take((size_t)B * kMaxCross * sizeof(unsigned long long));
     size_t o_xbox = take((size_t)B * kMaxCross * sizeof(float4));
     if (ws) {
@@ -594,7 +610,8 @@ static int ensure_kernel_attributes() {
     set((const void *)score_kernel<false>, kScoreSmemLimit);
     set((const void *)score_kernel_simple<true>, kScoreSmemLimit / kStages);
     set((const void *)score_kernel_simple<false>, kScoreSmemLimit / kStages);
-    set((const void *)nms_fast_kernel, kFastSmemBytes);
+    set((const void *)nms_fast_kernel<4>, FastCfg<4>::kSmem);
+    set((const void *)nms_fast_kernel<8>, FastCfg<8>::kSmem);
     set((const void *)nms_general_kernel, kNmsSmemLimit);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -605,11 +622,26 @@ static int ensure_kernel_attributes() {
     return PLYOLO_OK;
 }
 
+// Class groups per image.  4 (512 threads x 3 candidates per CTA) is the layout in use.  The 8-group layout (256 threads
+// x 4) is kept behind PLYOLO_NMS_GROUPS=8 as a measured negative result: bit-identical, but its phases are latency-
+// rather than issue-bound, so an image's NMS is not shorter (17.8 vs 15.6 us after its last tile), and a cluster of 8
+// needs 8 free SMs of one GPC beside the score CTAs: only 16 images are resident at a time (cfg2: 69.7 vs 45.0 us).
+static bool no_device_launch() {
+    static const bool v = [] { const char *e = getenv("PLYOLO_NO_CDP"); return e && e[0] == '1'; }();
+    return v;
+}
+
+static int nms_groups_for(int B) {
+    (void)B;
+    static const int forced = [] { const char *v = getenv("PLYOLO_NMS_GROUPS"); return v ? atoi(v) : 0; }();
+    return forced == 8 ? 8 : 4;
+}
+
 // `overlap`: the score stage was the persistent kernel (it triggers its dependents at once and publishes the
 // per-image scored-tile counters), so the class-split NMS may start under it.
 static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
                    const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream,
-                   int variant = PLYOLO_NMS_YOLOX, int n_peers = 0, float *const *peer_dets = nullptr,
+                   int ng, int variant = PLYOLO_NMS_YOLOX, int n_peers = 0, float *const *peer_dets = nullptr,
                    int32_t *const *peer_counts = nullptr) {
     NmsParams np;
     np.n_peers = n_peers;
@@ -640,11 +672,22 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     const bool pdl = pdl_enabled();
     record_stage_event(1, stream);
     if (g_skip_nms) return PLYOLO_OK;  // debug: time the score stage alone
+    // device-side launches of the general path only outside stream capture (see nms_general_kernel); PLYOLO_NO_CDP=1
+    // forces the host-launched variant everywhere
+    bool host_general = no_device_launch();
+    if (split && !host_general) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
+        host_general = cs != cudaStreamCaptureStatusNone;
+    }
+    np.device_launch = host_general ? 0 : 1;
     if (split) {
         np.wait_tiles = overlap ? 1 : 0;
         np.all_general = 0;
-        const cudaError_t e = launch_ex(nms_fast_kernel, dim3(kGroups, B), dim3(kFastThreads), kFastSmemBytes, stream,
-                                        pdl && overlap, np);
+        const cudaError_t e = ng == 8 ? launch_ex(nms_fast_kernel<8>, dim3(8, B), dim3(FastCfg<8>::kThreads), FastCfg<8>::kSmem, stream,
+                                                  pdl && overlap, np)
+                                      : launch_ex(nms_fast_kernel<4>, dim3(4, B), dim3(FastCfg<4>::kThreads), FastCfg<4>::kSmem, stream,
+                                                  pdl && overlap, np);
         if (e != cudaSuccess) {
             set_error("nms_fast_kernel: %s", cudaGetErrorString(e));
             cudaGetLastError();
@@ -652,14 +695,16 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
         }
         count_launch();
     }
-    if (split) {  // the class-split kernel launches the general path itself, per image, when it has to
+    if (split && !host_general) {  // the class-split kernel launches the general path itself, per image, when it has to
         record_stage_event(2, stream);
         return PLYOLO_OK;
     }
     np.wait_tiles = 0;
     np.all_general = split ? 0 : 1;
     np.prof = nullptr;
-    const cudaError_t e = launch_ex(nms_general_kernel, dim3(B), dim3(kNmsThreads), smem, stream, pdl && split, np);
+    // behind the class-split kernel: a plain (fully ordered) launch — its 180 KB CTAs must not sit on SMs while the
+    // class-split clusters still need them
+    const cudaError_t e = launch_ex(nms_general_kernel, dim3(B), dim3(kNmsThreads), smem, stream, false, np);
     if (e != cudaSuccess) {
         set_error("nms_general_kernel: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -776,13 +821,14 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (A & 3) == 0) ? 1 : 0;
     sp.prof = nullptr;
     sp.variant = PLYOLO_NMS_YOLOX;
+    sp.ng = nms_groups_for(B);
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   overlap, (cudaStream_t)stream);
+                   overlap, (cudaStream_t)stream, sp.ng);
 }
 
 extern "C" int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl, const int *hs, const int *ws,
@@ -811,12 +857,13 @@ extern "C" int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl,
     sp.bulk_ok = bulk ? 1 : 0;
     sp.prof = g_score_prof;
     sp.variant = PLYOLO_NMS_YOLOX;
+    sp.ng = nms_groups_for(B);
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<true>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   overlap, (cudaStream_t)stream, PLYOLO_NMS_YOLOX, n_peers, host_peer_dets, host_peer_counts);
+                   overlap, (cudaStream_t)stream, sp.ng, PLYOLO_NMS_YOLOX, n_peers, host_peer_dets, host_peer_counts);
 }
 
 extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
@@ -847,11 +894,12 @@ extern "C" int plyolo_postprocess_yolo_f32(const float *preds, int B, int N, int
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (N & 3) == 0) ? 1 : 0;
     sp.prof = nullptr;
     sp.variant = variant;
+    sp.ng = 4;
     sp.lv.n = 0; sp.lv.A = N;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, N, sp.NT, nms_thre, class_agnostic, max_nms, max_det, 0, sp.ws, dets, counts, keep_idx, overlap,
-                   (cudaStream_t)stream, variant);
+                   (cudaStream_t)stream, sp.ng, variant);
 }

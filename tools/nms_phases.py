@@ -6,7 +6,8 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pl_yolo_b200 import _lib, ops, synth
 
-B, G = int(os.environ.get("NMS_B", "32")), 4
+B = int(os.environ.get("NMS_B", "32"))
+G = int(os.environ.get("PLYOLO_NMS_GROUPS", "8" if B * 8 <= 296 else "4"))
 size = int(os.environ.get("NMS_SIZE", "640"))
 heads = [torch.from_numpy(h).cuda() for h in synth.make_heads(B, size, 80, seed=int(sys.argv[1]) if len(sys.argv) > 1 else 0)]
 L = _lib.lib()
@@ -42,5 +43,5 @@ t0 = t_flag.min()
 print("image: tiles complete at / NMS done at (us after the first image's tiles were complete)")
 print("  " + "  ".join("%d: %.1f/%.1f" % (b, (t_flag[b] - t0) / 1e3, (t_end[b] - t0) / 1e3) for b in range(0, B, max(1, B // 16))))
 print("  last image's tiles complete at %.1f us; last NMS done at %.1f us -> exposed tail %.1f us" % ((t_flag.max() - t0) / 1e3, (t_end.max() - t0) / 1e3, (t_end.max() - t_flag.max()) / 1e3))
-print("ncross", ctr[:, 5].tolist())
-print("general-path flags", ctr[:, 6].tolist(), "tiles done", ctr[:, 7].tolist()[:4])
+print("ncross", ctr[:, 9].tolist())
+print("general-path flags", ctr[:, 10].tolist(), "tiles done", ctr[:, 11].tolist()[:4])
