@@ -63,11 +63,12 @@ int make_levels(Levels &lv, const float *const *host_lvl, const int *hs, const i
         lv.off[l] = off;
         lv.tile0[l] = t0;
         lv.stride[l] = (float)strides[l];
+        lv.inv_w[l] = 1.0f / (float)ws[l];
         off += lv.hw[l];
         t0 += (lv.hw[l] + tile - 1) / tile;
     }
     for (int l = n_levels; l < PLYOLO_MAX_LEVELS; ++l) {
-        lv.ptr[l] = nullptr; lv.hw[l] = 0; lv.w[l] = 1; lv.off[l] = off; lv.tile0[l] = t0; lv.stride[l] = 1.f;
+        lv.ptr[l] = nullptr; lv.hw[l] = 0; lv.w[l] = 1; lv.off[l] = off; lv.tile0[l] = t0; lv.stride[l] = 1.f; lv.inv_w[l] = 1.f;
     }
     lv.tile0[n_levels] = t0;
     for (int l = n_levels + 1; l <= PLYOLO_MAX_LEVELS; ++l) lv.tile0[l] = t0;

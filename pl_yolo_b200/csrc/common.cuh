@@ -46,6 +46,7 @@ struct Levels {
     int off[PLYOLO_MAX_LEVELS];        // first anchor index of the level
     int tile0[PLYOLO_MAX_LEVELS + 1];  // first tile index of the level (per-level tiling)
     float stride[PLYOLO_MAX_LEVELS];
+    float inv_w[PLYOLO_MAX_LEVELS];    // 1 / W (fp32)
     int n;
     int A;
 };

@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 L.plyolo_debug_score_profile(None)
 p = prof.cpu().numpy().astype(np.float64)
 tiles = p[:, :, 7].sum()
-names = {1: "wait for data", 2: "class sweep + box", 3: "release barrier", 4: "ballots + barrier", 5: "slots, atomics, barrier", 6: "bucket writes"}
+names = {1: "wait for data", 2: "class sweep + box", 4: "release, ballots, atomics issued, barrier", 5: "slot records", 6: "bucket records"}
 tot = 0
 for k, n in names.items():
     us = p[:, :, k].sum() / tiles / 1965.0
