@@ -203,10 +203,21 @@ def run_reference(args, rank):
                          "simota_img_per_s": sim_v, "simota_sample": "best of 2 passes x 32 images of cfg3 (%.1f s each)" % min(sim_ts)},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or a library: NCCL's version banner)
+    writes to fd 1 was redirected to stderr at start-up."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -230,6 +241,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land in front of the JSON line
         dist.init_process_group("nccl", device_id=dev)
         if os.environ.get("BENCH_EXCHANGE") == "nccl":  # leave the communication kernel SMs to run on
             os.environ.setdefault("PLYOLO_SCORE_SMS_RESERVED", "2")
@@ -315,12 +327,13 @@ def main():
         n_sets = len(heads)
         # N > 1: the detection exchange of every step, into peer-mapped gathered buffers (CUDA IPC over NVLink,
         # pl_yolo_b200.distributed.PeerDetections), one cross-rank fence per round of steps.  BENCH_EXCHANGE=
-        #   dma (default): every step's finished block is pushed to the other ranks by the copy engines on a side stream,
-        #                  under the next step's score kernel — no SM, no collective kernel;
-        #   stores:        the NMS kernels store every row to the peers themselves (plyolo_decode_postprocess_bcast_f32);
+        #   stores (default): the NMS kernels store every row to the peers themselves (plyolo_decode_postprocess_bcast_f32:
+        #                  compute and collective in one kernel); with several batches in flight the remote stores of one
+        #                  batch's last images run under the next batches' score kernels;
+        #   dma:           every step's finished block is pushed to the other ranks by the copy engines on a side stream;
         #   nccl:          one NCCL all-gather of the fused buffer per step on a side stream.
         pdx = None
-        xmode = os.environ.get("BENCH_EXCHANGE", "dma")  # dma | stores | nccl
+        xmode = os.environ.get("BENCH_EXCHANGE", "stores")  # stores | dma | nccl
         if exchange and xmode in ("dma", "stores"):
             try:
                 pdx = PeerDetections(b_loc, 300, dev, slots=n_sets)
@@ -389,8 +402,9 @@ def main():
         # stream join at the end of the round.  One replay per round also keeps the host (graph launch + NCCL enqueue per
         # step would cost more than the device work of a step) out of the measurement.
         round_graph = None
-        # steps per round (one join / one fence per round): up to 8 passes over the input sets, dividing `steps`
-        mult = max([m for m in range(1, 9) if steps % (n_sets * m) == 0] or [1])
+        # steps per round (one join / one fence per round: the pipeline of batches in flight drains there): up to 32 passes
+        # over the input sets, dividing `steps`
+        mult = max([m for m in range(1, 33) if steps % (n_sets * m) == 0] or [1])
         R_STEPS = n_sets * mult
         if graphs is not None:
             try:
@@ -708,7 +722,7 @@ def main():
             line["cuda_baseline"] = cuda_base
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         for t in peer_tables:
             t.close()
