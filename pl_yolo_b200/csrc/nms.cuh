@@ -137,6 +137,12 @@ __device__ __forceinline__ void store_row6(const NmsParams &p, const int b, cons
         q[0] = r0; q[1] = r1; q[2] = r2;
     }
 }
+// the caller's buffers only (the class-split kernel ships the finished image block to the peers in one coalesced pass)
+__device__ __forceinline__ void store_row6_local(const NmsParams &p, const int b, const int row, const float2 r0, const float2 r1,
+                                                 const float2 r2) {
+    float2 *d = reinterpret_cast<float2 *>(p.dets + ((size_t)b * p.max_det + row) * 6);
+    d[0] = r0; d[1] = r1; d[2] = r2;
+}
 __device__ __forceinline__ void store_count(const NmsParams &p, const int b, const int n) {
     p.counts[b] = n;
     for (int r = 0; r < p.n_peers; ++r) p.peer_counts[r][b] = n;

@@ -500,16 +500,31 @@ __global__ void __cluster_dims__(NG, 1, 1) __maxnreg__(FastCfg<NG>::kRegs) nms_f
             const int bi = kidx2[i];
             const float4 bx = sbox[bi];
             const float sc = ordered_float(~(unsigned)(key >> kFastAnchorBits));  // the key holds the score bits
-            store_row6(p, b, rank, make_float2(bx.x, bx.y), make_float2(bx.z, bx.w), make_float2(sc, (float)scls[bi]));
+            store_row6_local(p, b, rank, make_float2(bx.x, bx.y), make_float2(bx.z, bx.w), make_float2(sc, (float)scls[bi]));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + rank] = (int)(key & ((1ull << kFastAnchorBits) - 1ull));
         }
     }
     if (g == 0) {
         for (int i = nkept + tid; i < p.max_det; i += kFastThreads) {
-            store_row6(p, b, i, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f));
+            store_row6_local(p, b, i, make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f));
             if (p.keep_idx) p.keep_idx[(size_t)b * p.max_det + i] = -1;
         }
         if (tid == 0) store_count(p, b, nkept);
+    }
+    if (p.n_peers > 0) {
+        // Multi-GPU exchange: the image's finished block [max_det, 6] goes to every peer's gathered buffer over NVLink.
+        // Row-by-row stores from the ranking threads (24 B at scattered rows, three partial sectors each) cost 1.3 us per
+        // peer and image — with 7 peers more than the NMS itself; instead the cluster waits for its rows to be complete
+        // (release / acquire at cluster scope), and every CTA copies a quarter of the block to every peer with fully
+        // coalesced 8-byte stores (256 B per warp instruction) read back from L2.
+        cluster.sync();
+        const int chunks = p.max_det * 3;  // float2 chunks of the block
+        const int per = (chunks + kGroups - 1) / kGroups, c0 = g * per, c1 = min(chunks, c0 + per);
+        const float2 *src = reinterpret_cast<const float2 *>(p.dets + (size_t)b * p.max_det * 6);
+        for (int w = tid; w < (c1 - c0) * p.n_peers; w += kFastThreads) {
+            const int r = w / (c1 - c0), c = c0 + (w - r * (c1 - c0));
+            reinterpret_cast<float2 *>(p.peer_dets[r] + (size_t)b * p.max_det * 6)[c] = __ldcg(src + c);
+        }
     }
     FPROF(8);
     if (prof && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[15] += 0; prof[12] = (long long)gt; }
