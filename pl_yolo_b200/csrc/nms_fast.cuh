@@ -27,7 +27,7 @@
 
 namespace plyolo {
 
-constexpr int kGC = 32;                               // arrays over class slots (>= kGCn)
+constexpr int kGC = 32;                               // class slots per group: class c -> slot c / kGroups
 #ifndef PLYOLO_NMS_ROUNDS
 #define PLYOLO_NMS_ROUNDS 4
 #endif
@@ -42,22 +42,18 @@ constexpr size_t kFastUnion = (size_t)(kAllKeys + 64) * 8;  // cross list | kept
 static_assert(kFastUnion >= (size_t)1536 * 2 && kFastUnion >= (size_t)kFastCross * 24, "union region too small");
 constexpr int kFastMaxDet = kKeys2Cap - 32;  // max_det the fast kernel supports
 
-// One image = one cluster of NG class-group CTAs.  Two layouts share the code below:
-//   NG = 4: 512 threads x 3 candidates (1536 per group), 48 registers — the layout in use;
-//   NG = 8: 256 threads x 4 candidates (1024 per group), 64 registers — experiment (PLYOLO_NMS_GROUPS=8, see
-//           nms_groups_for in postprocess.cu: exact, not faster).
-template <int NG>
-struct FastCfg {
-    static_assert(NG == 4 || NG == 8, "4 or 8 class groups per image");
-    static constexpr int kThreads = 2048 / NG;
-    static constexpr int kWarps = kThreads / 32;
-    static constexpr int kPer = NG == 4 ? 3 : 4;           // candidates per thread
-    static constexpr int kCap = kThreads * kPer;           // candidates per (image, class group)
-    static constexpr int kGCn = kMaxClasses / NG;          // class slots per group: class c -> slot c / NG
-    static constexpr int kRegs = NG == 4 ? 48 : 64;
-    static constexpr int kXPer = kMaxCross / kThreads;     // cross-list entries per thread
-    static constexpr size_t kSmem = (size_t)kCap * 25 + kFastUnion + (size_t)kKeys2Cap * 10;
-};
+// One image = one cluster of kGroups class-group CTAs: 512 threads x 3 candidates (1536 per group), 48 registers.
+// (An 8-group layout — 256 threads x 4, clusters of 8 — was measured in round 2: bit-identical, but the phases are
+// latency- rather than issue-bound, so an image's NMS was not shorter (17.8 vs 15.6 us after its last tile), and a
+// cluster of 8 needs 8 free SMs of one GPC beside the score CTAs: cfg2 69.7 vs 45.0 us.  Removed.)
+constexpr int kFastThreads = 512;
+constexpr int kFastPer = 3;                           // candidates per thread
+constexpr int kFastCapG = kFastThreads * kFastPer;    // candidates per (image, class group) the kernel stages
+constexpr int kFastRegs = 48;
+constexpr int kXPer = kMaxCross / kFastThreads;       // cross-list entries per thread
+static_assert(kFastCapG <= kBucketCap && kFastCapG <= (1 << kIdxBits), "layout assumptions");
+// dynamic shared memory: skey[cap] u64 | sbox[cap] float4 | scls[cap] u8 | union | keys2[kKeys2Cap] u64 | kidx2 u16
+constexpr size_t kFastSmemBytes = (size_t)kFastCapG * 25 + kFastUnion + (size_t)kKeys2Cap * 10;
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
@@ -84,11 +80,8 @@ __device__ __forceinline__ void launch_general_for(const NmsParams &p, const int
 }
 
 // Register budget of the co-residency (per SM sub-partition: 16384 registers): the score CTA puts 5 of its 18 warps on
-// one sub-partition, this CTA 4 of its 16 (NG = 4) or 2 of its 8 (NG = 8): 5 * 32 * kScoreRegs + 4 * 32 * 48 <= 16384.
-template <int NG>
-__global__ void __cluster_dims__(NG, 1, 1) __maxnreg__(FastCfg<NG>::kRegs) nms_fast_kernel(const NmsParams p) {
-    constexpr int kGroups = NG, kFastThreads = FastCfg<NG>::kThreads, kFastPer = FastCfg<NG>::kPer;
-    constexpr int kFastCapG = FastCfg<NG>::kCap, kGCn = FastCfg<NG>::kGCn, kXPer = FastCfg<NG>::kXPer;
+// one sub-partition, this CTA 4 of its 16: 5 * 32 * kScoreRegs + 4 * 32 * kFastRegs <= 16384.
+__global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char fsm[];
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(fsm);                       // [cap] class segments
     float4 *sbox = reinterpret_cast<float4 *>(fsm + (size_t)kFastCapG * 8);                        // [cap] by box index, un-offset
@@ -119,7 +112,7 @@ __global__ void __cluster_dims__(NG, 1, 1) __maxnreg__(FastCfg<NG>::kRegs) nms_f
     FPROF(0);
 
     // ---- wait until every tile of the image has been scored (the score kernel may still be running)
-    if (tid < kGC) {  // (slots >= kGCn stay empty)
+    if (tid < kGC) {
 #pragma unroll
         for (int r = 0; r < kFastRounds; ++r) { c_best_hi[r][tid] = 0xffffffffu; c_best_lo[r][tid] = 0xffffffffu; }
         g_cnt[tid] = 0;
@@ -140,8 +133,8 @@ __global__ void __cluster_dims__(NG, 1, 1) __maxnreg__(FastCfg<NG>::kRegs) nms_f
 
     // the bucket is read before its fill count is known (entries past the count are stale bytes of the caller-owned
     // workspace, never used): one L2 round trip for counters, keys and boxes instead of two
-    const unsigned long long *bucket = p.ws.gkey + (size_t)b * kBucketImg + g * (kBucketImg / kGroups);
-    const float4 *bbox = p.ws.gbox + (size_t)b * kBucketImg + g * (kBucketImg / kGroups);
+    const unsigned long long *bucket = p.ws.gkey + (size_t)b * kBucketImg + g * kBucketCap;
+    const float4 *bbox = p.ws.gbox + (size_t)b * kBucketImg + g * kBucketCap;
     unsigned long long nk[kFastPer];
     int cl[kFastPer];
     float4 xb_spec[kXPer];

@@ -28,18 +28,19 @@
 namespace plyolo {
 
 constexpr int kPpTile = 128;
-constexpr int kMaxGroups = 8;    // class groups per image: 4 (class & 3) or 8 (class & 7), one NMS CTA each (ScoreParams::ng)
+constexpr int kGroups = 4;      // class groups per image (class & 3): one NMS CTA each
 constexpr int kMaxCross = 512;  // boxes that may reach into another class's offset range (x1, y1 < -0.5)
 constexpr int kFastCap = 4096;  // candidates per NMS CTA whose boxes are staged in shared memory
 constexpr int kImgCtr = 16;     // ints per image in the counter block (zeroed before every call)
-// counter block of an image: [0, kMaxGroups) candidates per class group, then
+// counter block of an image: [0, kGroups) candidates per class group, then
 constexpr int kCtrMaxCoord = 8;  // largest coordinate (ordered uint): tv:ops/boxes.py:99
 constexpr int kCtrCross = 9;     // boxes listed in the cross list
 constexpr int kCtrGeneral = 10;  // the image must be redone by the general path
 constexpr int kCtrDone = 11;     // tiles of the image that have been scored (released by the score kernel)
 constexpr int kCtrMaxX2 = 12;    // largest x2 / y2 of the image's candidates (ordered uint): bounds which cross boxes
 constexpr int kCtrMaxY2 = 13;    //   can reach another class's offset range at all
-constexpr int kBucketImg = 8192; // bucket entries per image: ng groups of kBucketImg / ng (the NMS kernels stage 1536 / 1024 of them)
+constexpr int kBucketCap = 2048; // bucket entries per (image, class group); the NMS kernel stages the first 1536 of them
+constexpr int kBucketImg = kGroups * kBucketCap;
 
 constexpr size_t kNmsSmemLimit = 190 * 1024;  // dynamic shared memory of the NMS kernels (33 KB are static)
 struct CandWs {
@@ -50,8 +51,8 @@ struct CandWs {
     float *aux;         // [B, NT*128]  second score of the YOLOv3 / YOLOv5 call sites (objectness / best class score)
     // per image: candidates bucketed by class group, in arrival order (the keys carry the anchor order)
     int *ctr;                     // [B, kImgCtr]  counter block (kCtr*)
-    unsigned long long *gkey;     // [B, ng, kBucketImg / ng]  class << 57 | ~ordered(score) << 25 | anchor
-    float4 *gbox;                 // [B, ng, kBucketImg / ng]  the same candidates' corners
+    unsigned long long *gkey;     // [B, kGroups, kBucketCap]  class << 57 | ~ordered(score) << 25 | anchor
+    float4 *gbox;                 // [B, kGroups, kBucketCap]  the same candidates' corners
     unsigned long long *xkey;     // [B, kMaxCross] keys of the cross boxes
     float4 *xbox;                 // [B, kMaxCross]
 };
@@ -62,7 +63,6 @@ struct ScoreParams {
     int B, A, C, ch, NT;
     float conf_thr;
     int bulk_ok;
-    int ng;       // class groups per image (4 or 8): which NMS kernel follows
     int variant;  // PLYOLO_NMS_YOLOX / _YOLOV3 / _YOLOV5: which reference call site's filter + score arithmetic (preds input only)
     CandWs ws;
     long long *prof;  // debug: [gridDim.x][kConsumers][8] accumulated cycles per consumer phase, or null
@@ -287,20 +287,19 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
     // order: the keys carry the anchor order) and the warp's largest x2 / y2 go into the image's maxima.  The atomics are
     // issued here, their results are used after the slot records below: the L2 round trip is hidden.
     const unsigned m = __ballot_sync(0xffffffffu, pass);
-    const int grp = cls & (p.ng - 1);
+    const int grp = cls & (kGroups - 1);
     int *ctr = p.ws.ctr + b * kImgCtr;
     unsigned gm = 0u;
     int gbase = 0;  // lane g: where the warp's candidates of class group g start in the bucket
     if (m) {        // uniform for the warp
         int gcnt = 0;
 #pragma unroll
-        for (int g = 0; g < kMaxGroups; ++g) {
-            if (g >= p.ng) break;  // uniform
+        for (int g = 0; g < kGroups; ++g) {
             const unsigned mg = __ballot_sync(0xffffffffu, pass && grp == g);
             if (lane == g) gcnt = __popc(mg);
             if (grp == g) gm = mg;
         }
-        if (gcnt) gbase = atomicAdd(&ctr[lane], gcnt);  // lanes < ng only
+        if (gcnt) gbase = atomicAdd(&ctr[lane], gcnt);  // lanes < kGroups only
         // maxima as ordered uints (NaN coordinates are ignored like fmaxf does); max over all four coordinates
         // (tv:ops/boxes.py:99): the fused decode gives x2 >= x1, y2 >= y1 (w, h = exp(..) * stride)
         unsigned oz = float_ordered(pass ? fmaxf(box.z, -3.0e38f) : -3.0e38f);
@@ -349,10 +348,9 @@ __device__ __forceinline__ void score_tile(const ScoreParams &p, const float *ti
             // the low bits order equal scores by anchor (ascending anchor == the reference's candidate order)
             const unsigned long long key = ((unsigned long long)cls << 57) |
                                            ((unsigned long long)(~float_ordered(conf)) << 25) | (unsigned)(tc.anchor_base + src_t);
-            const int gcap = kBucketImg / p.ng;
-            if (pos < gcap) {  // a fuller group is redone by the general path from the slot arrays
-                p.ws.gkey[(size_t)b * kBucketImg + grp * gcap + pos] = key;
-                p.ws.gbox[(size_t)b * kBucketImg + grp * gcap + pos] = box;
+            if (pos < kBucketCap) {  // a fuller group is redone by the general path from the slot arrays
+                p.ws.gkey[(size_t)b * kBucketImg + grp * kBucketCap + pos] = key;
+                p.ws.gbox[(size_t)b * kBucketImg + grp * kBucketCap + pos] = box;
             }
             if (box.x < -0.5f && box.y < -0.5f) {
                 const int xi = atomicAdd(&ctr[kCtrCross], 1);
@@ -669,8 +667,7 @@ static int ensure_kernel_attributes() {
     set((const void *)score_kernel<false>, kScoreSmemLimit);
     set((const void *)score_kernel_simple<true>, kScoreSmemLimit / kStages);
     set((const void *)score_kernel_simple<false>, kScoreSmemLimit / kStages);
-    set((const void *)nms_fast_kernel<4>, FastCfg<4>::kSmem);
-    set((const void *)nms_fast_kernel<8>, FastCfg<8>::kSmem);
+    set((const void *)nms_fast_kernel, kFastSmemBytes);
     set((const void *)nms_general_kernel, kNmsSmemLimit);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -681,26 +678,16 @@ static int ensure_kernel_attributes() {
     return PLYOLO_OK;
 }
 
-// Class groups per image.  4 (512 threads x 3 candidates per CTA) is the layout in use.  The 8-group layout (256 threads
-// x 4) is kept behind PLYOLO_NMS_GROUPS=8 as a measured negative result: bit-identical, but its phases are latency-
-// rather than issue-bound, so an image's NMS is not shorter (17.8 vs 15.6 us after its last tile), and a cluster of 8
-// needs 8 free SMs of one GPC beside the score CTAs: only 16 images are resident at a time (cfg2: 69.7 vs 45.0 us).
 static bool no_device_launch() {
     static const bool v = [] { const char *e = getenv("PLYOLO_NO_CDP"); return e && e[0] == '1'; }();
     return v;
-}
-
-static int nms_groups_for(int B) {
-    (void)B;
-    static const int forced = [] { const char *v = getenv("PLYOLO_NMS_GROUPS"); return v ? atoi(v) : 0; }();
-    return forced == 8 ? 8 : 4;
 }
 
 // `overlap`: the score stage was the persistent kernel (it triggers its dependents at once and publishes the
 // per-image scored-tile counters), so the class-split NMS may start under it.
 static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, int max_nms, int max_det, int flavor,
                    const CandWs &ws, float *dets, int32_t *counts, int32_t *keep_idx, bool overlap, cudaStream_t stream,
-                   int ng, int variant = PLYOLO_NMS_YOLOX, int n_peers = 0, float *const *peer_dets = nullptr,
+                   int variant = PLYOLO_NMS_YOLOX, int n_peers = 0, float *const *peer_dets = nullptr,
                    int32_t *const *peer_counts = nullptr) {
     NmsParams np;
     np.n_peers = n_peers;
@@ -743,10 +730,8 @@ static int run_nms(int B, int A, int NT, double nms_thre, int class_agnostic, in
     if (split) {
         np.wait_tiles = overlap ? 1 : 0;
         np.all_general = 0;
-        const cudaError_t e = ng == 8 ? launch_ex(nms_fast_kernel<8>, dim3(8, B), dim3(FastCfg<8>::kThreads), FastCfg<8>::kSmem, stream,
-                                                  pdl && overlap, np)
-                                      : launch_ex(nms_fast_kernel<4>, dim3(4, B), dim3(FastCfg<4>::kThreads), FastCfg<4>::kSmem, stream,
-                                                  pdl && overlap, np);
+        const cudaError_t e = launch_ex(nms_fast_kernel, dim3(kGroups, B), dim3(kFastThreads), kFastSmemBytes, stream,
+                                        pdl && overlap, np);
         if (e != cudaSuccess) {
             set_error("nms_fast_kernel: %s", cudaGetErrorString(e));
             cudaGetLastError();
@@ -880,14 +865,13 @@ extern "C" int plyolo_postprocess_f32(const float *preds, int B, int A, int C, d
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (A & 3) == 0) ? 1 : 0;
     sp.prof = nullptr;
     sp.variant = PLYOLO_NMS_YOLOX;
-    sp.ng = nms_groups_for(B);
     sp.lv.n = 0; sp.lv.A = A;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   overlap, (cudaStream_t)stream, sp.ng);
+                   overlap, (cudaStream_t)stream);
 }
 
 extern "C" int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl, const int *hs, const int *ws,
@@ -916,13 +900,12 @@ extern "C" int plyolo_decode_postprocess_bcast_f32(const float *const *host_lvl,
     sp.bulk_ok = bulk ? 1 : 0;
     sp.prof = g_score_prof;
     sp.variant = PLYOLO_NMS_YOLOX;
-    sp.ng = nms_groups_for(B);
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<true>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, A, sp.NT, nms_thre, class_agnostic, max_nms, max_det, flavor, sp.ws, dets, counts, keep_idx,
-                   overlap, (cudaStream_t)stream, sp.ng, PLYOLO_NMS_YOLOX, n_peers, host_peer_dets, host_peer_counts);
+                   overlap, (cudaStream_t)stream, PLYOLO_NMS_YOLOX, n_peers, host_peer_dets, host_peer_counts);
 }
 
 extern "C" int plyolo_decode_postprocess_f32(const float *const *host_lvl, const int *hs, const int *ws,
@@ -953,12 +936,11 @@ extern "C" int plyolo_postprocess_yolo_f32(const float *preds, int B, int N, int
     sp.bulk_ok = (((uintptr_t)preds & 15) == 0 && (N & 3) == 0) ? 1 : 0;
     sp.prof = nullptr;
     sp.variant = variant;
-    sp.ng = 4;
     sp.lv.n = 0; sp.lv.A = N;
     cand_ws_layout(B, sp.NT, &sp.ws, static_cast<unsigned char *>(workspace));
     bool overlap = false;
     rc = launch_score<false>(sp, (cudaStream_t)stream, &overlap);
     if (rc != PLYOLO_OK) return rc;
     return run_nms(B, N, sp.NT, nms_thre, class_agnostic, max_nms, max_det, 0, sp.ws, dets, counts, keep_idx, overlap,
-                   (cudaStream_t)stream, sp.ng, variant);
+                   (cudaStream_t)stream, variant);
 }

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pl_yolo_b200 import _lib, ops, synth
 
 B = int(os.environ.get("NMS_B", "32"))
-G = int(os.environ.get("PLYOLO_NMS_GROUPS", "8" if B * 8 <= 296 else "4"))
+G = 4  # class groups per image (kGroups)
 size = int(os.environ.get("NMS_SIZE", "640"))
 heads = [torch.from_numpy(h).cuda() for h in synth.make_heads(B, size, 80, seed=int(sys.argv[1]) if len(sys.argv) > 1 else 0)]
 L = _lib.lib()
