@@ -79,7 +79,7 @@ __device__ __forceinline__ void launch_general_for(const NmsParams &p, const int
     nms_general_kernel<<<1, kNmsThreads, p.general_smem, cudaStreamFireAndForget>>>(q);
 }
 
-// Register budget of the co-residency (per SM sub-partition: 16384 registers): the score CTA puts 5 of its 18 warps on
+// Register budget of the co-residency (per SM sub-partition: 16384 registers): the score CTA puts at most 5 of its 19 warps on
 // one sub-partition, this CTA 4 of its 16: 5 * 32 * kScoreRegs + 4 * 32 * kFastRegs <= 16384.
 __global__ void __cluster_dims__(kGroups, 1, 1) __maxnreg__(kFastRegs) nms_fast_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char fsm[];

@@ -9,14 +9,19 @@
 //   of 16 classes; a conservative pre-filter that can only over-admit; for the admitted anchors the exact max /
 //   first argmax over the sigmoid VALUES (T1) inside the rounding window of the fp32 sigmoid;
 //   conf = sigmoid(obj) * class_conf, conf >= thr in fp32.  The survivors are compacted IN ANCHOR ORDER (warp
-//   ballot + prefix) into the tile's slot range of the candidate arrays and bucketed by class group.
+//   ballot + prefix, the tile's ONE group barrier) into the tile's slot range of the candidate arrays and bucketed by
+//   class group (per-warp atomics, issued right after the sweep).  Every warp releases the stage on its own; a
+//   publisher warp releases the per-image scored-tile counters at GPU scope for stage 2.
 // Stage 2  nms_fast_kernel       one 4-CTA cluster per image (nms_fast.cuh), launched with programmatic dependent
 //   launch so that it runs UNDER stage 1: small CTAs (512 threads, 52 KB) co-resident with the score CTAs, every
 //   cluster starts when its image's scored-tile counter is complete.  Per-class pre-kill, sorts and greedy sweeps
 //   with torchvision's arithmetic (coordinate-trick offsets, asymmetric FMA, IEEE division; see `suppresses`),
 //   kept lists merged by rank through distributed shared memory.
 // Stage 3  nms_general_kernel    one CTA per image (nms.cuh: global sort + bit-matrix rounds), only for the images
-//   the class split cannot handle exactly (flag per image; exits at once otherwise).
+//   the class split cannot handle exactly: launched from the device by stage 2 for those images (plain stream launches)
+//   or by the host behind stage 2 under stream capture (flag per image; exits at once otherwise).
+// Several batches can be in flight on different streams (pl_yolo_b200/pipeline.py): the workspace is per call, and
+// stage 1 / stage 2 CTAs of different batches share the SMs the same way.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -648,7 +653,7 @@ static int sm_count() {
 }
 
 // Per-device, once: the kernels' shared-memory limits (fixed maxima, so that no launch ever lowers another thread's
-// limit) and the maximal shared-memory carveout — the score CTA (171.5 KB) and the NMS CTA (53.5 KB) only fit on
+// limit) and the maximal shared-memory carveout — the score CTA (171.5 KB) and the NMS CTA (54.3 KB) only fit on
 // one SM together when the SM is configured for 228 KB of shared memory.
 constexpr size_t kScoreSmemLimit = (size_t)kStages * kPpTile * (5 + PLYOLO_MAX_CLASSES) * sizeof(float);  // 192 KB
 static int ensure_kernel_attributes() {
