@@ -217,7 +217,7 @@ int plyolo_voc_tpfp_f32(const float *dets, const int32_t *counts, int B, int max
                         plyolo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * loss tail of YOLOXLoss (N2) — replaces models/losses/yolox/yolox_loss.py:121-163 for use_l1 == False: the
+ * loss tail of YOLOXLoss (N2) — replaces models/losses/yolox/yolox_loss.py:121-163 (the use_l1 term: plyolo_yolox_l1_f32 below): the
  * per-image target building (:123-127, :142-147), IOUloss(loss_type="giou")
  * (models/layers/losses/iou_loss.py:7-50) on the foreground anchors, BCEWithLogitsLoss on the objectness of
  * all B*A anchors (:152) and on the classes of the foreground anchors (:154).
@@ -242,6 +242,20 @@ int plyolo_yolox_loss_backward_f32(const float *preds, const float *labels, cons
                                    const int32_t *matched_gt, const float *matched_iou, int B, int C, int Lmax,
                                    const float *grad_sums, float *const *host_grad_lvl, const int *hs,
                                    const int *ws, const int *strides, int n_levels, plyolo_stream_t stream);
+
+/* use_l1 term of the loss tail (yolox_loss.py:128-133, :158; get_l1_type :373-378): sum over the foreground anchors of
+ * |raw regression output - (gx / s - grid_x, gy / s - grid_y, log(gw / s + 1e-8), log(gh / s + 1e-8))|
+ * (the reference's loss_l1 is this divided by max(sum num_fg, 1)).
+ *   ori    [B, A, 4] fp32 device, 16-byte aligned: the second output of plyolo_decode_f32(inference=0)
+ *   sum    [1] fp32 device;  workspace: plyolo_yolox_loss_workspace_bytes(B, A)
+ * Backward: grad_sum[0] * sign(ori - target) is ADDED to the four regression planes of the head-map gradients
+ * (call it after plyolo_yolox_loss_backward_f32, which overwrites them). */
+int plyolo_yolox_l1_f32(const float *ori, const float *labels, const uint8_t *fg_mask, const int32_t *matched_gt, int B,
+                        int Lmax, const int *hs, const int *ws, const int *strides, int n_levels, float *sum,
+                        void *workspace, size_t workspace_bytes, plyolo_stream_t stream);
+int plyolo_yolox_l1_backward_f32(const float *ori, const float *labels, const uint8_t *fg_mask, const int32_t *matched_gt,
+                                 int B, int C, int Lmax, const float *grad_sum, float *const *host_grad_lvl, const int *hs,
+                                 const int *ws, const int *strides, int n_levels, plyolo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -252,17 +252,17 @@ def simota_cases():
 
 
 # ------------------------------------------------------------------------------- loss tail gradients (N2)
-def gen_lossgrad(name, B, size, seed_h, seed_l, max_labels, C=80):
+def gen_lossgrad(name, B, size, seed_h, seed_l, max_labels, C=80, use_l1=False):
     """The real reference's training loss and its autograd gradients with respect to the head outputs
     (YOLOXLoss.__call__ in training mode, yolox_loss.py:20-173; decode mutates its inputs in place, quirk Q1, so the
     leaves are cloned first)."""
     heads = synth.make_heads(B, size, C, seed_h)
     labels = synth.make_labels(B, size, max_labels, C, seed_l)
     leaves = [T(h).clone().requires_grad_(True) for h in heads]
-    out = YOLOXLoss(C, STRIDES)([x.clone() for x in leaves], T(labels))
+    out = YOLOXLoss(C, STRIDES, use_l1=use_l1)([x.clone() for x in leaves], T(labels))
     out["loss"].backward()
     losses = {k: float(v) for k, v in out.items()}
-    save(name, dict(kind="lossgrad", B=B, size=size, C=C, strides=STRIDES, seed_heads=seed_h,
+    save(name, dict(kind="lossgrad", B=B, size=size, C=C, strides=STRIDES, seed_heads=seed_h, use_l1=bool(use_l1),
                     labels=dict(gen="synth", seed=seed_l, max_labels=max_labels, min_gt=1, max_gt=None),
                     sha_heads=synth.digest(*heads), sha_labels=synth.digest(labels), losses=losses),
          **{"grad%d" % l: x.grad.numpy() for l, x in enumerate(leaves)})
@@ -281,3 +281,6 @@ if __name__ == "__main__":
     if "lossgrad" in which:  # added with N2; not part of the default set so the older fixtures stay byte-identical
         gen_lossgrad("lossgrad_160_b2", 2, 160, 51, 52, 12)
         gen_lossgrad("lossgrad_320_b2", 2, 320, 53, 54, 40)
+    if "lossgrad_l1" in which:  # use_l1=True (the reference's own configs never enable it)
+        gen_lossgrad("lossgrad_l1_160_b2", 2, 160, 55, 56, 12, use_l1=True)
+        gen_lossgrad("lossgrad_l1_320_b3", 3, 320, 57, 58, 30, use_l1=True)

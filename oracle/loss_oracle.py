@@ -62,9 +62,10 @@ def giou_loss_and_grad(p: np.ndarray, g: np.ndarray):
 
 
 def loss_tail(preds: np.ndarray, labels: np.ndarray, assign: Dict[str, np.ndarray], hw: Sequence[Sequence[int]],
-              strides: Sequence[int]):
+              strides: Sequence[int], ori: np.ndarray = None):
     """preds [B,A,5+C] training-mode decode output, assign = the SimOTA result (fg_mask, matched_gt, matched_iou, num_fg,
-    num_gt).  -> (loss dict, [d loss / d head map l as [B,5+C,H,W]])."""
+    num_gt).  -> (loss dict, [d loss / d head map l as [B,5+C,H,W]]).  ori [B,A,4] = the raw regression outputs: with it the
+    use_l1 term (yolox_loss.py:128-133, :158, get_l1_type :373-378) is added."""
     preds = preds.astype(np.float64)
     labels = labels.astype(np.float64)
     B, A, ch = preds.shape
@@ -82,8 +83,20 @@ def loss_tail(preds: np.ndarray, labels: np.ndarray, assign: Dict[str, np.ndarra
     s_obj = _bce_logits(preds[..., 4], obj_t).sum()
     s_cls = _bce_logits(preds[b_idx, a_idx, 5:], tcls).sum()
     loss_iou, loss_obj, loss_cls = s_iou / num_fgs, s_obj / num_fgs, s_cls / num_fgs
-    losses = {"loss": 5.0 * loss_iou + loss_obj + loss_cls, "loss_iou": loss_iou, "loss_obj": loss_obj, "loss_cls": loss_cls,
-              "loss_l1": 0.0, "proportion": num_fgs / max(num_gts, 1)}
+    loss_l1, gl1 = 0.0, None
+    if ori is not None:
+        ori = ori.astype(np.float64)
+        sv = np.concatenate([np.full(H * W, float(st)) for (H, W), st in zip(hw, strides)])            # expanded_strides
+        xs = np.concatenate([np.tile(np.arange(W, dtype=np.float64), H) for (H, W) in hw])              # x_shifts
+        ys = np.concatenate([np.repeat(np.arange(H, dtype=np.float64), W) for (H, W) in hw])            # y_shifts
+        st = sv[a_idx]
+        t = np.stack([matched[:, 1] / st - xs[a_idx], matched[:, 2] / st - ys[a_idx],
+                      np.log(matched[:, 3] / st + 1e-8), np.log(matched[:, 4] / st + 1e-8)], 1)         # get_l1_type
+        d = ori[b_idx, a_idx] - t
+        loss_l1 = np.abs(d).sum() / num_fgs                                                               # :158
+        gl1 = np.sign(d) / num_fgs
+    losses = {"loss": 5.0 * loss_iou + loss_obj + loss_cls + loss_l1, "loss_iou": loss_iou, "loss_obj": loss_obj,
+              "loss_cls": loss_cls, "loss_l1": loss_l1, "proportion": num_fgs / max(num_gts, 1)}
     # d loss / d preds
     gp = np.zeros_like(preds)
     gp[..., 4] = (_sigmoid(preds[..., 4]) - obj_t) / num_fgs
@@ -97,6 +110,10 @@ def loss_tail(preds: np.ndarray, labels: np.ndarray, assign: Dict[str, np.ndarra
         gl = gp[:, off:off + n].copy()
         gl[..., 0:2] *= s
         gl[..., 2:4] *= preds[:, off:off + n, 2:4]
+        if gl1 is not None:  # the raw outputs receive the L1 gradient directly
+            g4 = np.zeros((B, A, 4))
+            g4[b_idx, a_idx] = gl1
+            gl[..., 0:4] += g4[:, off:off + n]
         grads.append(gl.transpose(0, 2, 1).reshape(B, ch, H, W))
         off += n
     return losses, grads

@@ -75,6 +75,10 @@ def _declare(lib):
     lib.plyolo_yolox_loss_backward_f32.restype = c_int
     lib.plyolo_yolox_loss_backward_f32.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp, POINTER(c_void_p), ip, ip,
                                                    ip, c_int, vp]
+    lib.plyolo_yolox_l1_f32.restype = c_int
+    lib.plyolo_yolox_l1_f32.argtypes = [vp, vp, vp, vp, c_int, c_int, ip, ip, ip, c_int, vp, vp, c_size_t, vp]
+    lib.plyolo_yolox_l1_backward_f32.restype = c_int
+    lib.plyolo_yolox_l1_backward_f32.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, vp, POINTER(c_void_p), ip, ip, ip, c_int, vp]
 
 
 def lib() -> ctypes.CDLL:

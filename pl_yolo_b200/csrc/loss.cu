@@ -248,6 +248,98 @@ __global__ void __launch_bounds__(kLossThreads) yolox_loss_bwd_kernel(const Loss
     }
 }
 
+
+// ---- use_l1 term (yolox_loss.py:128-133, :158; get_l1_type :373-378) ------------------------------------------------
+// L1 distance between the RAW regression outputs of the foreground anchors and the matched GT expressed in the head's
+// own units: (gx / s - grid_x, gy / s - grid_y, log(gw / s + 1e-8), log(gh / s + 1e-8)).
+struct L1Params {
+    const float *ori;      // [B,A,4] raw regression outputs (second output of the training-mode decode)
+    const float *labels;   // [B,Lmax,5]
+    const uint8_t *fg;     // [B,A]
+    const int32_t *mg;     // [B,A]
+    Levels lv;             // geometry; bwd: ptr[l] = gradient of head map l (accumulated into)
+    int B, A, Lmax, ch;
+    float *partial;        // fwd: [B * ceil(A / kLossThreads)]
+    const float *gscale;   // bwd: [1] device, upstream gradient of the sum
+};
+
+// target and level / cell of anchor a (a foreground anchor of image b)
+__device__ __forceinline__ void l1_target(const L1Params &p, const int b, const int a, const size_t row, float (&t)[4], int &l,
+                                          int &cell) {
+    l = 0;
+#pragma unroll
+    for (int i = 1; i < PLYOLO_MAX_LEVELS; ++i)
+        if (i < p.lv.n && a >= p.lv.off[i]) l = i;
+    cell = a - p.lv.off[l];
+    const int W = p.lv.w[l], gy = cell / W, gx = cell - gy * W;
+    const float s = p.lv.stride[l];
+    const float *L = p.labels + ((size_t)b * p.Lmax + p.mg[row]) * 5;
+    t[0] = L[1] / s - (float)gx;          // :374
+    t[1] = L[2] / s - (float)gy;          // :375
+    t[2] = logf(L[3] / s + 1e-8f);        // :376
+    t[3] = logf(L[4] / s + 1e-8f);        // :377
+}
+
+__global__ void __launch_bounds__(kLossThreads) yolox_l1_fwd_kernel(const L1Params p) {
+    __shared__ float red[kLossThreads / 32];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a = blockIdx.x * kLossThreads + tid;
+    const size_t row = (size_t)b * p.A + (a < p.A ? a : 0);
+    float v = 0.f;
+    if (a < p.A && p.fg[row] != 0) {
+        float t[4];
+        int l, cell;
+        l1_target(p, b, a, row, t, l, cell);
+        const float4 o = *reinterpret_cast<const float4 *>(p.ori + row * 4);
+        v = ((fabsf(o.x - t[0]) + fabsf(o.y - t[1])) + fabsf(o.z - t[2])) + fabsf(o.w - t[3]);  // nn.L1Loss(reduction="none")
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLossThreads / 32; ++w) sum += red[w];
+        p.partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sum;
+    }
+}
+
+// sum[0] = sum of partial[i], fixed order: 256 strided accumulators, then a tree
+__global__ void __launch_bounds__(256) yolox_l1_reduce_kernel(const float *partial, const int n, float *sum) {
+    __shared__ float sh[256];
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) v += partial[i];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sum[0] = sh[0];
+}
+
+// d(sum * g) / d(raw outputs) = g * sign(ori - target), added to the regression planes of the head-map gradients
+__global__ void __launch_bounds__(kLossThreads) yolox_l1_bwd_kernel(const L1Params p) {
+    const int b = blockIdx.y, a = blockIdx.x * kLossThreads + threadIdx.x;
+    if (a >= p.A) return;
+    const size_t row = (size_t)b * p.A + a;
+    if (p.fg[row] == 0) return;
+    float t[4];
+    int l, cell;
+    l1_target(p, b, a, row, t, l, cell);
+    const float4 o = *reinterpret_cast<const float4 *>(p.ori + row * 4);
+    const float g = p.gscale[0];
+    const float d[4] = {o.x - t[0], o.y - t[1], o.z - t[2], o.w - t[3]};
+    const int hw = p.lv.hw[l];
+    float *dst = const_cast<float *>(p.lv.ptr[l]) + (size_t)b * p.ch * hw + cell;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float sg = d[c] > 0.f ? 1.0f : (d[c] < 0.f ? -1.0f : 0.f);  // sign(); NaN -> 0 like torch.sign's comparison form
+        dst[(size_t)c * hw] += g * sg;
+    }
+}
+
 static size_t loss_partials(int B, int A) { return (size_t)B * ((A + kLossThreads - 1) / kLossThreads); }
 
 }  // namespace plyolo
@@ -317,5 +409,68 @@ extern "C" int plyolo_yolox_loss_backward_f32(const float *preds, const float *l
     if (first_use_on_device(1)) cudaFuncSetAttribute(yolox_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     yolox_loss_bwd_kernel<<<dim3(p.lv.tile0[p.lv.n], B), kLossThreads, smem, (cudaStream_t)stream>>>(p);
     PLYOLO_CHECK_LAUNCH("yolox_loss_bwd_kernel");
+    return PLYOLO_OK;
+}
+
+static int check_l1_args(const float *ori, const float *labels, const uint8_t *fg_mask, const int32_t *matched_gt, int B, int Lmax) {
+    using namespace plyolo;
+    PLYOLO_REQUIRE(ori && labels && fg_mask && matched_gt, "an input pointer is null");
+    PLYOLO_REQUIRE(((uintptr_t)ori & 15) == 0, "ori must be 16-byte aligned");
+    PLYOLO_REQUIRE(B >= 1 && B <= 65535, "B=%d not in [1,65535]", B);
+    PLYOLO_REQUIRE(Lmax >= 1 && Lmax <= 32767, "Lmax=%d not in [1,32767]", Lmax);
+    return PLYOLO_OK;
+}
+
+extern "C" int plyolo_yolox_l1_f32(const float *ori, const float *labels, const uint8_t *fg_mask, const int32_t *matched_gt,
+                                   int B, int Lmax, const int *hs, const int *ws, const int *strides, int n_levels,
+                                   float *sum, void *workspace, size_t workspace_bytes, plyolo_stream_t stream) {
+    using namespace plyolo;
+    L1Params p;
+    const float *none[PLYOLO_MAX_LEVELS] = {nullptr};
+    PLYOLO_REQUIRE(n_levels >= 1 && n_levels <= PLYOLO_MAX_LEVELS, "n_levels=%d not in [1,%d]", n_levels, PLYOLO_MAX_LEVELS);
+    for (int l = 0; l < n_levels; ++l) none[l] = ori;  // make_levels wants non-null level pointers: unused by the forward
+    int rc = make_levels(p.lv, none, hs, ws, strides, n_levels, kLossTile);
+    if (rc != PLYOLO_OK) return rc;
+    rc = check_l1_args(ori, labels, fg_mask, matched_gt, B, Lmax);
+    if (rc != PLYOLO_OK) return rc;
+    PLYOLO_REQUIRE(sum != nullptr, "sum is null");
+    const int A = p.lv.A;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < plyolo_yolox_loss_workspace_bytes(B, A)) {
+        set_error("workspace null, not 256-byte aligned, or smaller than plyolo_yolox_loss_workspace_bytes()");
+        return PLYOLO_ERR_WORKSPACE;
+    }
+    rc = check_device();
+    if (rc != PLYOLO_OK) return rc;
+    p.ori = ori; p.labels = labels; p.fg = fg_mask; p.mg = matched_gt;
+    p.B = B; p.A = A; p.Lmax = Lmax; p.ch = 0;
+    p.partial = static_cast<float *>(workspace); p.gscale = nullptr;
+    const dim3 grid((A + kLossThreads - 1) / kLossThreads, B);
+    yolox_l1_fwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(p);
+    PLYOLO_CHECK_LAUNCH("yolox_l1_fwd_kernel");
+    yolox_l1_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p.partial, (int)loss_partials(B, A), sum);
+    PLYOLO_CHECK_LAUNCH("yolox_l1_reduce_kernel");
+    return PLYOLO_OK;
+}
+
+extern "C" int plyolo_yolox_l1_backward_f32(const float *ori, const float *labels, const uint8_t *fg_mask,
+                                            const int32_t *matched_gt, int B, int C, int Lmax, const float *grad_sum,
+                                            float *const *host_grad_lvl, const int *hs, const int *ws, const int *strides,
+                                            int n_levels, plyolo_stream_t stream) {
+    using namespace plyolo;
+    L1Params p;
+    int rc = make_levels(p.lv, const_cast<const float *const *>(host_grad_lvl), hs, ws, strides, n_levels, kLossTile);
+    if (rc != PLYOLO_OK) return rc;
+    rc = check_l1_args(ori, labels, fg_mask, matched_gt, B, Lmax);
+    if (rc != PLYOLO_OK) return rc;
+    PLYOLO_REQUIRE(C >= 1 && C <= PLYOLO_MAX_CLASSES, "C=%d not in [1,%d]", C, PLYOLO_MAX_CLASSES);
+    PLYOLO_REQUIRE(grad_sum != nullptr, "grad_sum is null");
+    rc = check_device();
+    if (rc != PLYOLO_OK) return rc;
+    p.ori = ori; p.labels = labels; p.fg = fg_mask; p.mg = matched_gt;
+    p.B = B; p.A = p.lv.A; p.Lmax = Lmax; p.ch = 5 + C;
+    p.partial = nullptr; p.gscale = grad_sum;
+    const dim3 grid((p.A + kLossThreads - 1) / kLossThreads, B);
+    yolox_l1_bwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(p);
+    PLYOLO_CHECK_LAUNCH("yolox_l1_bwd_kernel");
     return PLYOLO_OK;
 }

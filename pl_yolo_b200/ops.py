@@ -342,6 +342,58 @@ def yolox_loss_backward_raw(preds: torch.Tensor, labels: torch.Tensor, fg_mask: 
     return grads
 
 
+def _l1_inputs(ori, labels, fg_mask, matched_gt, hw):
+    o = _check_cuda_f32(ori, "ori")
+    lab = _check_cuda_f32(labels, "labels")
+    if o.dim() != 3 or o.shape[2] != 4 or lab.dim() != 3 or lab.shape[2] != 5 or lab.shape[0] != o.shape[0]:
+        raise ValueError("ori must be [B, A, 4] and labels [B, Lmax, 5]")
+    if fg_mask.shape != o.shape[:2] or matched_gt.shape != o.shape[:2]:
+        raise ValueError("fg_mask / matched_gt must be [B, A]")
+    if fg_mask.dtype not in (torch.bool, torch.uint8) or matched_gt.dtype != torch.int32:
+        raise TypeError("fg_mask must be bool / uint8 and matched_gt int32")
+    hs, ws_ = list(hw[0::2]), list(hw[1::2])
+    if sum(h * w for h, w in zip(hs, ws_)) != o.shape[1]:
+        raise ValueError("the level shapes do not add up to A")
+    return o, lab, fg_mask.contiguous(), matched_gt.contiguous(), hs, ws_
+
+
+def yolox_l1_sum_raw(ori: torch.Tensor, labels: torch.Tensor, fg_mask: torch.Tensor, matched_gt: torch.Tensor, hw: List[int],
+                     strides: List[int]) -> torch.Tensor:
+    """use_l1 term (yolox_loss.py:128-133, :158): -> [1] = sum over the foreground anchors of |ori - get_l1_type(matched GT)|."""
+    o, lab, fg, mg, hs, ws_ = _l1_inputs(ori, labels, fg_mask, matched_gt, hw)
+    B, A, _ = o.shape
+    dev = o.device
+    out = torch.empty((1,), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _workspace("loss", L.plyolo_yolox_loss_workspace_bytes(B, A), dev)
+        rc = L.plyolo_yolox_l1_f32(o.data_ptr(), lab.data_ptr(), fg.data_ptr(), mg.data_ptr(), B, lab.shape[1], _lib.int_array(hs),
+                                   _lib.int_array(ws_), _lib.int_array(strides), len(hs), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(dev))
+    _lib.check(rc, "plyolo_yolox_l1_f32")
+    return out
+
+
+def yolox_l1_backward_raw(ori: torch.Tensor, labels: torch.Tensor, fg_mask: torch.Tensor, matched_gt: torch.Tensor,
+                          grad_sum: torch.Tensor, grads: List[torch.Tensor], hw: List[int], strides: List[int]) -> None:
+    """Adds grad_sum * sign(ori - target) to the regression planes of the head-map gradients `grads` (in place)."""
+    o, lab, fg, mg, hs, ws_ = _l1_inputs(ori, labels, fg_mask, matched_gt, hw)
+    g = _check_cuda_f32(grad_sum, "grad_sum")
+    if g.numel() != 1:
+        raise ValueError("grad_sum must have 1 element")
+    B = o.shape[0]
+    for t, h, w in zip(grads, hs, ws_):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.shape[0] != B or t.shape[2:] != (h, w):
+            raise ValueError("grads must be contiguous fp32 CUDA tensors [B, 5+C, H, W], one per level")
+    dev = o.device
+    with torch.cuda.device(dev):
+        rc = _lib.lib().plyolo_yolox_l1_backward_f32(
+            o.data_ptr(), lab.data_ptr(), fg.data_ptr(), mg.data_ptr(), B, int(grads[0].shape[1]) - 5, lab.shape[1], g.data_ptr(),
+            _lib.ptr_array([t.data_ptr() for t in grads]), _lib.int_array(hs), _lib.int_array(ws_), _lib.int_array(strides),
+            len(hs), _stream_ptr(dev))
+    _lib.check(rc, "plyolo_yolox_l1_backward_f32")
+
+
 yolox_loss_sums = torch.library.custom_op("plyolo::yolox_loss_sums", yolox_loss_sums_raw, mutates_args=())
 
 

@@ -8,8 +8,9 @@ still reaches the head), and the per-image / per-GT Python loops of the SimOTA a
 (:54-118, ~14k launches and ~4k host syncs per batch of 32) are three kernel launches for the whole
 batch.  The loss tail (:121-173) runs fused as well (N2): one forward kernel produces the three loss sums, one
 backward kernel writes d(loss)/d(head maps) directly (decode backward folded in) — the [B,A,5+C] gradient tensor and
-the reference's gathered / concatenated target tensors never exist.  `use_l1=True` and `fused_loss=False` keep the
-batched torch code for the tail (same values; the torch path is what the fused kernels are tested against).
+the reference's gathered / concatenated target tensors never exist; `use_l1=True` adds one small kernel each way
+(:128-133, :158).  `fused_loss=False` keeps the batched torch code for the tail (same values; the torch path is what
+the fused kernels are also tested against).
 """
 from __future__ import annotations
 
@@ -53,13 +54,13 @@ class _DecodeTrain(torch.autograd.Function):
 
 
 class _FusedTrainLoss(torch.autograd.Function):
-    """(sum GIoU, sum obj BCE, sum cls BCE) [3], num_fg [B], num_gt [B] = decode -> SimOTA -> loss tail of the head maps;
-    backward: one kernel straight into the head maps (yolox_loss.py:22, :43-154)."""
+    """(sum GIoU, sum obj BCE, sum cls BCE[, sum L1]) [3 or 4], num_fg [B], num_gt [B] = decode -> SimOTA -> loss tail of the
+    head maps; backward: one kernel straight into the head maps (+ the L1 signs) (yolox_loss.py:22, :43-158)."""
 
     @staticmethod
-    def forward(ctx, strides, labels, *inputs):
+    def forward(ctx, strides, use_l1, labels, *inputs):
         strides = list(strides)
-        preds, _ = ops.decode_raw(list(inputs), strides, False)
+        preds, ori = ops.decode_raw(list(inputs), strides, False)
         hw: List[int] = []
         for x in inputs:
             hw += [int(x.shape[2]), int(x.shape[3])]
@@ -68,16 +69,21 @@ class _FusedTrainLoss(torch.autograd.Function):
             labels = labels.new_zeros((labels.shape[0], 1, 5))
         fg, mg, miou, nfg, ngt = ops.simota_assign_raw(preds, labels, hw, strides)
         sums = ops.yolox_loss_sums_raw(preds, labels, fg, mg, miou)
-        ctx.strides, ctx.hw = strides, hw
-        ctx.save_for_backward(preds, labels, fg, mg, miou)
+        if use_l1:                                                 # :128-133, :158
+            sums = torch.cat([sums, ops.yolox_l1_sum_raw(ori, labels, fg, mg, hw, strides)])
+        ctx.strides, ctx.hw, ctx.use_l1 = strides, hw, bool(use_l1)
+        ctx.save_for_backward(preds, labels, fg, mg, miou, ori if use_l1 else preds.new_empty(0))
         ctx.mark_non_differentiable(nfg, ngt)
         return sums, nfg, ngt
 
     @staticmethod
     def backward(ctx, g_sums, _g_nfg, _g_ngt):
-        preds, labels, fg, mg, miou = ctx.saved_tensors
-        grads = ops.yolox_loss_backward_raw(preds, labels, fg, mg, miou, g_sums.contiguous(), ctx.hw, ctx.strides)
-        return (None, None, *grads)
+        preds, labels, fg, mg, miou, ori = ctx.saved_tensors
+        g_sums = g_sums.contiguous()
+        grads = ops.yolox_loss_backward_raw(preds, labels, fg, mg, miou, g_sums[:3].contiguous(), ctx.hw, ctx.strides)
+        if ctx.use_l1:
+            ops.yolox_l1_backward_raw(ori, labels, fg, mg, g_sums[3:4].contiguous(), grads, ctx.hw, ctx.strides)
+        return (None, None, None, *grads)
 
 
 class YOLOXLoss(nn.Module):
@@ -88,7 +94,7 @@ class YOLOXLoss(nn.Module):
         self.n_anchors = 1
         self.use_l1 = use_l1
         self.lazy_eval = lazy_eval  # eval mode returns LazyPredictions (fused decode+NMS route)
-        self.fused_loss = fused_loss  # training: loss tail + backward as kernels (N2); needs use_l1 == False
+        self.fused_loss = fused_loss  # training: loss tail + backward as kernels (N2), use_l1 included
         self.bcewithlog_loss = nn.BCEWithLogitsLoss(reduction="none")
         self.l1_loss = nn.L1Loss(reduction="none")
         self._grid_cache = {}
@@ -138,22 +144,22 @@ class YOLOXLoss(nn.Module):
             return ops.simota_assign_raw(preds.detach(), labels.to(preds.dtype), hw, list(self.strides))
 
     def _train_fused(self, inputs, labels):
-        """yolox_loss.py:20-173 for use_l1 == False: three sums from the kernels, the scalar arithmetic of :148-171 here."""
+        """yolox_loss.py:20-173: the sums from the kernels, the scalar arithmetic of :148-171 here."""
         inputs = list(inputs)
-        sums, nfg, ngt = _FusedTrainLoss.apply(tuple(self.strides), labels, *inputs)
+        sums, nfg, ngt = _FusedTrainLoss.apply(tuple(self.strides), bool(self.use_l1), labels, *inputs)
         counts = torch.stack([nfg.sum(), ngt.sum()]).tolist()     # one host sync (the reference has thousands)
         num_fgs = max(int(counts[0]), 1)                           # :148
         num_gts = int(counts[1])
         loss_iou = sums[0] / num_fgs                               # :150
         loss_obj = sums[1] / num_fgs                               # :152
         loss_cls = sums[2] / num_fgs                               # :154
-        loss_l1 = 0.0                                              # :160
+        loss_l1 = sums[3] / num_fgs if self.use_l1 else 0.0      # :158-160
         loss = 5.0 * loss_iou + loss_obj + loss_cls + loss_l1      # :162-163
         return {"loss": loss, "loss_iou": loss_iou, "loss_obj": loss_obj, "loss_cls": loss_cls, "loss_l1": loss_l1,
                 "proportion": num_fgs / max(num_gts, 1)}
 
     def _train(self, inputs, labels):
-        if self.fused_loss and not self.use_l1:
+        if self.fused_loss:
             return self._train_fused(inputs, labels)
         preds, oriboxes, x_shifts, y_shifts, expanded_strides = self.decode(inputs)
         B, A, _ = preds.shape

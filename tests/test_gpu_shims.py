@@ -118,12 +118,42 @@ def test_fused_loss_vs_real_reference_gradients(name):
     meta, g = load(name)
     heads = [cu(h).requires_grad_(True) for h in heads_of(meta)]
     labels = cu(labels_of(meta, g))
-    out = YOLOXLoss(80, STRIDES)(heads, labels)
+    out = YOLOXLoss(80, STRIDES, use_l1=bool(meta.get("use_l1", False)))(heads, labels)
     for k, v in meta["losses"].items():
         assert float(out[k]) == pytest.approx(v, rel=2e-5, abs=1e-6), k
     out["loss"].backward()
     for l, h in enumerate(heads):
         _grad_close(h.grad, cu(g["grad%d" % l]), "%s level %d" % (name, l))
+
+
+def test_fused_l1_term_vs_torch_tail():
+    """use_l1=True: the fused kernels (sum + sign gradient into the raw regression planes) against the batched torch tail,
+    the L1 term alone and inside the total loss; an image without GTs; the stand-alone ops' argument checks."""
+    B, size = 3, 320
+    heads = synth.make_heads(B, size, 80, 61)
+    lab = synth.make_labels(B, size, 25, 80, 62)
+    lab[2] = 0
+    labels = cu(lab)
+    for pick in ("loss_l1", "loss"):
+        a = [cu(h).requires_grad_(True) for h in heads]
+        b = [cu(h).requires_grad_(True) for h in heads]
+        f = YOLOXLoss(80, STRIDES, use_l1=True)(a, labels)
+        g = YOLOXLoss(80, STRIDES, use_l1=True, fused_loss=False)(b, labels)
+        for k in ("loss", "loss_iou", "loss_obj", "loss_cls", "loss_l1", "proportion"):
+            assert float(torch.as_tensor(f[k]).detach()) == pytest.approx(float(torch.as_tensor(g[k]).detach()), rel=1e-5, abs=1e-7), k
+        assert float(f["loss_l1"]) > 0
+        f[pick].backward()
+        g[pick].backward()
+        for l, (x, y) in enumerate(zip(a, b)):
+            _grad_close(x.grad, y.grad, "%s level %d" % (pick, l))
+    from pl_yolo_b200 import ops
+    preds, ori = ops.decode_raw([cu(h) for h in heads], STRIDES, False)
+    hw = [v for s in STRIDES for v in (size // s, size // s)]
+    fg, mg, _, _, _ = ops.simota_assign_raw(preds, labels, hw, STRIDES)
+    with pytest.raises(ValueError):
+        ops.yolox_l1_sum_raw(ori[:, :-1], labels, fg, mg, hw, STRIDES)
+    with pytest.raises(TypeError):
+        ops.yolox_l1_sum_raw(ori.double(), labels, fg, mg, hw, STRIDES)
 
 
 @pytest.mark.parametrize("C", [1, 20, 91])
