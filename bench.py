@@ -552,7 +552,7 @@ def main():
         try:
             lo, hi = shard_range(256, rank, world)
             b4 = hi - lo
-            h4np, l4np = make_inputs(batch=b4, n_sets=2)
+            h4np, l4np = make_inputs(batch=b4, n_sets=2 if b4 > 64 else 4)  # as many input sets as batches in flight
             h4, l4 = to_dev(h4np, l4np)
             r = bench_decode_nms(h4, b4, SIZE, Ke, exchange=world > 1)
             s4 = bench_simota(h4, l4, b4, SIZE, Ke)
