@@ -547,6 +547,10 @@ __device__ void resolve_conflict(const SimParams &p, const int b, const int a, c
     __syncwarp();
 }
 
+#ifndef PLYOLO_SWEEP_OCC
+#define PLYOLO_SWEEP_OCC 4  // resident sweep CTAs per SM the register allocation is sized for (5 / 6: 48 / 40 registers with
+                            // spills, measured 89.0 / 90.9 us per SimOTA call against 88.3: no gain)
+#endif
 // ---- K2a: IoU sweep ---------------------------------------------------------------------------
 // kSweepSub warps per GT (kSweepGts GTs of one image per CTA).  Every warp tests the union boxes of the image's
 // candidate groups 32 at a time and visits its share of the groups the GT overlaps (all other pairs have
@@ -630,7 +634,7 @@ __device__ __forceinline__ void lane_insert(float (&t)[kLaneTop], float a) {
     t[kLaneTop - 1] = fmaxf(t[kLaneTop - 1], a);
 }
 
-__global__ void __launch_bounds__(kSweepThreads, 4) simota_sweep_kernel(const SimParams p) {
+__global__ void __launch_bounds__(kSweepThreads, PLYOLO_SWEEP_OCC) simota_sweep_kernel(const SimParams p) {
     __shared__ float s_list[kSweepGts][kSweepSub - 1][kLaneTop][32];
     __shared__ int s_seen[kSweepGts][kSweepSub - 1][32];
     __shared__ unsigned short s_hit[kSweepGts][kSweepChunk];
